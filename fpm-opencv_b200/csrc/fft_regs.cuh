@@ -1,0 +1,137 @@
+// fft_regs.cuh -- in-register complex FFT butterflies of size 2,3,4,5,8,16 (fp32).
+// Natural-order in, natural-order out; INV=false: exp(-2*pi*i*jk/R) (cv::dft forward,
+// SURVEY 8c R1), INV=true: exp(+...), unscaled.  All indices are compile-time so the
+// arrays live in registers.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fpm {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+// multiply by -i (forward quarter turn) or +i (inverse)
+template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+// multiply by twiddle w (forward table) or its conjugate
+template <bool INV> __device__ __forceinline__ float2 twmul(float2 a, float2 w) {
+  return INV ? cmulc(a, w) : cmul(a, w);
+}
+
+template <bool INV> __device__ __forceinline__ void fft2(float2& a, float2& b) {
+  float2 t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
+}
+
+template <bool INV> __device__ __forceinline__ void fft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+  float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = rot90<INV>(csub(x1, x3));
+  x0 = cadd(t0, t2);
+  x2 = csub(t0, t2);
+  x1 = cadd(t1, t3);
+  x3 = csub(t1, t3);
+}
+
+template <bool INV> __device__ __forceinline__ void fft3(float2& x0, float2& x1, float2& x2) {
+  const float s = INV ? 0.86602540378443864676f : -0.86602540378443864676f;   // Im(W3)
+  float2 t1 = cadd(x1, x2);
+  float2 t2 = make_float2(fmaf(-0.5f, t1.x, x0.x), fmaf(-0.5f, t1.y, x0.y));
+  float2 d = csub(x1, x2);
+  float2 t3 = make_float2(-s * d.y, s * d.x);      // i*s*d
+  x0 = cadd(x0, t1);
+  x1 = cadd(t2, t3);
+  x2 = csub(t2, t3);
+}
+
+template <bool INV> __device__ __forceinline__ void fft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;    // cos(2pi/5), cos(4pi/5)
+  const float s1 = INV ? 0.95105651629515357212f : -0.95105651629515357212f;  // +-sin(2pi/5)
+  const float s2 = INV ? 0.58778525229247312917f : -0.58778525229247312917f;  // +-sin(4pi/5)
+  float2 a1 = cadd(x1, x4), b1 = csub(x1, x4), a2 = cadd(x2, x3), b2 = csub(x2, x3);
+  float2 y0 = cadd(x0, cadd(a1, a2));
+  float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
+  float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
+  // q = i*(s1*b1 + s2*b2),  r = i*(s2*b1 - s1*b2)
+  float2 q = make_float2(-(s1 * b1.y + s2 * b2.y), s1 * b1.x + s2 * b2.x);
+  float2 r = make_float2(-(s2 * b1.y - s1 * b2.y), s2 * b1.x - s1 * b2.x);
+  x0 = y0;
+  x1 = cadd(p1, q);
+  x4 = csub(p1, q);
+  x2 = cadd(p2, r);
+  x3 = csub(p2, r);
+}
+
+// (1 -+ i)/sqrt2 and (-1 -+ i)/sqrt2 multiplications
+template <bool INV> __device__ __forceinline__ float2 mulW8_1(float2 a) {
+  const float h = 0.70710678118654752440f;
+  return INV ? make_float2(h * (a.x - a.y), h * (a.x + a.y)) : make_float2(h * (a.x + a.y), h * (a.y - a.x));
+}
+template <bool INV> __device__ __forceinline__ float2 mulW8_3(float2 a) {
+  const float h = 0.70710678118654752440f;
+  return INV ? make_float2(-h * (a.x + a.y), h * (a.x - a.y)) : make_float2(h * (a.y - a.x), -h * (a.x + a.y));
+}
+
+template <bool INV> __device__ __forceinline__ void fft8(float2 (&v)[8]) {
+  // DIT: even / odd quarter transforms, then W8^k combine
+  fft4<INV>(v[0], v[2], v[4], v[6]);
+  fft4<INV>(v[1], v[3], v[5], v[7]);
+  // after fft4 the outputs sit in slots (0,2,4,6) = E0..E3 and (1,3,5,7) = O0..O3
+  float2 o0 = v[1], o1 = mulW8_1<INV>(v[3]), o2 = rot90<INV>(v[5]), o3 = mulW8_3<INV>(v[7]);
+  float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// multiply by W16^n (forward) or its conjugate, n compile-time in [0,9]
+template <bool INV, int n> __device__ __forceinline__ float2 mulW16(float2 a) {
+  if constexpr (n == 0) return a;
+  else if constexpr (n == 2) return mulW8_1<INV>(a);
+  else if constexpr (n == 4) return rot90<INV>(a);
+  else if constexpr (n == 6) return mulW8_3<INV>(a);
+  else {
+    constexpr float c = (n == 1) ? 0.92387953251128675613f : (n == 3) ? 0.38268343236508977173f : -0.92387953251128675613f;  // n==9
+    constexpr float s = (n == 1) ? -0.38268343236508977173f : (n == 3) ? -0.92387953251128675613f : 0.38268343236508977173f;
+    return twmul<INV>(a, make_float2(c, s));
+  }
+}
+
+template <bool INV> __device__ __forceinline__ void fft16(float2 (&v)[16]) {
+  // radix-4 DIT: four stride-4 sub-transforms A_j (j = 0..3) ...
+  fft4<INV>(v[0], v[4], v[8], v[12]);
+  fft4<INV>(v[1], v[5], v[9], v[13]);
+  fft4<INV>(v[2], v[6], v[10], v[14]);
+  fft4<INV>(v[3], v[7], v[11], v[15]);
+  // A_j[k] now sits in v[j + 4k]; twiddle by W16^(j*k)
+  v[5] = mulW16<INV, 1>(v[5]);   v[6] = mulW16<INV, 2>(v[6]);    v[7] = mulW16<INV, 3>(v[7]);
+  v[9] = mulW16<INV, 2>(v[9]);   v[10] = mulW16<INV, 4>(v[10]);  v[11] = mulW16<INV, 6>(v[11]);
+  v[13] = mulW16<INV, 3>(v[13]); v[14] = mulW16<INV, 6>(v[14]);  v[15] = mulW16<INV, 9>(v[15]);
+  // ... then for every k a 4-point transform over j gives X[k + 4q], q = 0..3 (in slots 4k+q)
+  fft4<INV>(v[0], v[1], v[2], v[3]);
+  fft4<INV>(v[4], v[5], v[6], v[7]);
+  fft4<INV>(v[8], v[9], v[10], v[11]);
+  fft4<INV>(v[12], v[13], v[14], v[15]);
+  // slot 4k+q holds X[k+4q]  ->  transpose the 4x4 index grid to natural order
+  float2 t;
+#define FPM_SWAP(a, b) t = v[a]; v[a] = v[b]; v[b] = t;
+  FPM_SWAP(1, 4) FPM_SWAP(2, 8) FPM_SWAP(3, 12) FPM_SWAP(6, 9) FPM_SWAP(7, 13) FPM_SWAP(11, 14)
+#undef FPM_SWAP
+}
+
+template <int R, bool INV> __device__ __forceinline__ void fftR(float2 (&v)[R]) {
+  if constexpr (R == 16) fft16<INV>(v);
+  else if constexpr (R == 8) fft8<INV>(v);
+  else if constexpr (R == 4) fft4<INV>(v[0], v[1], v[2], v[3]);
+  else if constexpr (R == 2) fft2<INV>(v[0], v[1]);
+  else static_assert(R == 16, "unsupported radix");
+}
+
+}  // namespace fpm

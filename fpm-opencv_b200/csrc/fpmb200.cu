@@ -1,0 +1,403 @@
+// fpmb200.cu -- C-ABI layer (include/fpmb200.h) over the sm_100a kernels of fpm_kernels.cuh.
+// Replaces the cv::UMat / cvComplex op sequence of runFPM() (fpmMain.cpp:274-498).
+// No CPU fallback: every entry point fails when no CUDA device can run the kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/fpmb200.h"
+#include "fpm_kernels.cuh"
+
+using namespace fpm;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(FPMB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct fpmb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int n_tiles = 0, N = 0, L = 0, n_leds = 0;
+  float delta1 = 5.f, delta2 = 10.f, eps = 1e-10f, kappa = 1.f;   // fpmMain.cpp:567-568, fpmMain.h:99
+  float2* objFc = nullptr;     // [n_tiles][L][L] centred
+  float2* objCrop = nullptr;   // [n_tiles][L][L]
+  float2* pupil = nullptr;     // [n_tiles][N][N]
+  uint16_t* stack = nullptr;   // [n_tiles][n_leds][N][N]
+  float* support = nullptr;    // [N][N]
+  short2* crop = nullptr;      // [n_leds]
+  float2* twN = nullptr;       // [N]
+  float2* twL = nullptr;       // [L]
+  float2* field_gmem = nullptr;
+  float2* scratch = nullptr;   // staging: max(L*L, init batch * N*N)
+  size_t scratch_elems = 0;
+  int ylo = 0, yhi = -1, xlo = 0, xhi = -1;
+  bool have_leds = false, have_support = false, have_stack = false;
+  // kernel variant
+  bool field_smem = false, p_smem = false;
+  int bs = 3;
+  size_t smem_bytes = 0;
+  int max_smem_optin = 0, sm_count = 0;
+  long long launches = 0;
+  char variant[160] = "unallocated";
+};
+
+extern "C" const char* fpmb200_last_error(void) { return g_err.c_str(); }
+extern "C" int fpmb200_abi_version(void) { return 1; }
+
+extern "C" int fpmb200_create(int device, fpmb200_ctx** out) {
+  if (!out) return fail(FPMB200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(FPMB200_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(FPMB200_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(FPMB200_ERR_CUDA, "device %d is sm_%d%d; libfpmb200 is built for sm_100a only", device, prop.major, prop.minor);
+  fpmb200_ctx* c = new fpmb200_ctx();
+  c->device = device;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return FPMB200_OK;
+}
+
+static void free_tiles(fpmb200_ctx* c) {
+  cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->support);
+  cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch);
+  c->objFc = c->objCrop = c->pupil = c->twN = c->twL = c->field_gmem = c->scratch = nullptr;
+  c->stack = nullptr; c->support = nullptr; c->crop = nullptr;
+  c->have_leds = c->have_support = c->have_stack = false;
+  c->n_tiles = 0;
+}
+
+extern "C" void fpmb200_destroy(fpmb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_tiles(c);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+static int upload_twiddles(float2* dst, int n) {
+  std::vector<float2> h(n);
+  for (int k = 0; k < n; ++k) {
+    double a = -2.0 * M_PI * (double)k / (double)n;
+    h[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  CK(cudaMemcpy(dst, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlarge, int n_leds) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  if (n_tiles <= 0 || n_leds <= 0) return fail(FPMB200_ERR_ARG, "n_tiles and n_leds must be positive");
+  if (Np != 64 && Np != 128 && Np != 256)
+    return fail(FPMB200_ERR_ARG, "Np=%d unsupported: the fused tile FFT handles 64, 128 and 256", Np);
+  if (Nlarge < Np || Nlarge % 64 != 0 || Nlarge > 8192)
+    return fail(FPMB200_ERR_ARG, "Nlarge=%d must be a multiple of 64 in [Np, 8192]", Nlarge);
+  {
+    int r = Nlarge;
+    for (int f : {2, 3, 5}) while (r % f == 0) r /= f;
+    if (r != 1) return fail(FPMB200_ERR_ARG, "Nlarge=%d has a prime factor other than 2,3,5", Nlarge);
+  }
+  CK(cudaSetDevice(c->device));
+  free_tiles(c);
+  c->n_tiles = n_tiles; c->N = Np; c->L = Nlarge; c->n_leds = n_leds;
+  const size_t LL = (size_t)Nlarge * Nlarge, NN = (size_t)Np * Np;
+  CK(cudaMalloc(&c->objFc, sizeof(float2) * LL * n_tiles));
+  CK(cudaMalloc(&c->objCrop, sizeof(float2) * LL * n_tiles));
+  CK(cudaMalloc(&c->pupil, sizeof(float2) * NN * n_tiles));
+  CK(cudaMalloc(&c->stack, sizeof(uint16_t) * NN * n_leds * n_tiles));
+  CK(cudaMalloc(&c->support, sizeof(float) * NN));
+  CK(cudaMalloc(&c->crop, sizeof(short2) * n_leds));
+  CK(cudaMalloc(&c->twN, sizeof(float2) * Np));
+  CK(cudaMalloc(&c->twL, sizeof(float2) * Nlarge));
+  c->scratch_elems = LL > NN * 64 ? LL : NN * 64;
+  CK(cudaMalloc(&c->scratch, sizeof(float2) * c->scratch_elems));
+  CK(cudaMemset(c->objFc, 0, sizeof(float2) * LL * n_tiles));
+  CK(cudaMemset(c->objCrop, 0, sizeof(float2) * LL * n_tiles));
+  CK(cudaMemset(c->pupil, 0, sizeof(float2) * NN * n_tiles));
+  int rc;
+  if ((rc = upload_twiddles(c->twN, Np)) != FPMB200_OK) return rc;
+  if ((rc = upload_twiddles(c->twL, Nlarge)) != FPMB200_OK) return rc;
+  snprintf(c->variant, sizeof c->variant, "allocated (support not uploaded yet)");
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_set_params(fpmb200_ctx* c, float delta1, float delta2, float eps, int literal_scalar) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  c->delta1 = delta1; c->delta2 = delta2; c->eps = eps; c->kappa = literal_scalar ? 1.f : 0.f;
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_upload_leds(fpmb200_ctx* c, const int16_t* cx, const int16_t* cy, int n_leds) {
+  if (!c || !cx || !cy) return fail(FPMB200_ERR_ARG, "NULL argument");
+  if (!c->n_tiles) return fail(FPMB200_ERR_STATE, "fpmb200_tiles_alloc first");
+  if (n_leds != c->n_leds) return fail(FPMB200_ERR_ARG, "n_leds=%d differs from the allocation (%d)", n_leds, c->n_leds);
+  std::vector<short2> h(n_leds);
+  for (int k = 0; k < n_leds; ++k) {
+    if (cx[k] < 0 || cy[k] < 0 || cx[k] + c->N > c->L || cy[k] + c->N > c->L)
+      return fail(FPMB200_ERR_ARG, "slot %d: crop origin (%d,%d) leaves the %dx%d spectrum", k, cx[k], cy[k], c->L, c->L);
+    h[k] = make_short2(cx[k], cy[k]);
+  }
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpy(c->crop, h.data(), sizeof(short2) * n_leds, cudaMemcpyHostToDevice));
+  c->have_leds = true;
+  return FPMB200_OK;
+}
+
+static size_t update_smem_bytes(const fpmb200_ctx* c, bool field_smem, bool p_smem, int bs) {
+  const int N = c->N, PITCH = N + 8;
+  const int NR = c->yhi - c->ylo + 1, NC = c->xhi - c->xlo + 1;
+  size_t b = 0;
+  if (field_smem) b += sizeof(float2) * N * PITCH;
+  if (p_smem) b += sizeof(float2) * NR * NC;
+  b += sizeof(float2) * N * 2 + sizeof(float) * 64;
+  b += sizeof(float) * (size_t)(c->L >> bs) * (c->L >> bs);
+  return b;
+}
+
+extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
+  if (!c || !mask) return fail(FPMB200_ERR_ARG, "NULL argument");
+  if (!c->n_tiles) return fail(FPMB200_ERR_STATE, "fpmb200_tiles_alloc first");
+  const int N = c->N, H = N / 2;
+  int ylo = H, yhi = -H - 1, xlo = H, xhi = -H - 1;
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j)
+      if (mask[i * N + j] != 0.f) {
+        int iw = i < H ? i : i - N, jw = j < H ? j : j - N;
+        if (iw < ylo) ylo = iw; if (iw > yhi) yhi = iw;
+        if (jw < xlo) xlo = jw; if (jw > xhi) xhi = jw;
+      }
+  if (yhi < ylo) return fail(FPMB200_ERR_ARG, "pupil support is empty");
+  c->ylo = ylo; c->yhi = yhi; c->xlo = xlo; c->xhi = xhi;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpy(c->support, mask, sizeof(float) * N * N, cudaMemcpyHostToDevice));
+  c->have_support = true;
+  // ---- choose the kernel variant for this (N, L, bbox) ----
+  const size_t cap = (size_t)c->max_smem_optin;
+  c->field_smem = (N <= 128);
+  int bs = 3;
+  while (bs < 5 && sizeof(float) * (size_t)(c->L >> bs) * (c->L >> bs) > 48 * 1024) ++bs;
+  c->bs = bs;
+  c->p_smem = update_smem_bytes(c, c->field_smem, true, bs) <= cap;
+  c->smem_bytes = update_smem_bytes(c, c->field_smem, c->p_smem, bs);
+  if (c->smem_bytes > cap)
+    return fail(FPMB200_ERR_ARG, "update kernel needs %zu B shared memory, device offers %zu", c->smem_bytes, cap);
+  if (!c->field_smem && !c->field_gmem)
+    CK(cudaMalloc(&c->field_gmem, sizeof(float2) * (size_t)N * (N + 8) * c->n_tiles));
+  snprintf(c->variant, sizeof c->variant,
+           "fpm_update_kernel<N=%d,field=%s,pupil=%s> bbox=[%d..%d]x[%d..%d] cell=%d smem=%zuB", N,
+           c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", ylo, yhi, xlo, xhi, 1 << bs, c->smem_bytes);
+  return FPMB200_OK;
+}
+
+static int check_range(fpmb200_ctx* c, int first, int n) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  if (!c->n_tiles) return fail(FPMB200_ERR_STATE, "fpmb200_tiles_alloc first");
+  if (first < 0 || n <= 0 || first + n > c->n_tiles)
+    return fail(FPMB200_ERR_ARG, "tile range [%d,%d) outside [0,%d)", first, first + n, c->n_tiles);
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_upload_stack(fpmb200_ctx* c, int first, int n, const uint16_t* stack, void* stream) {
+  int rc = check_range(c, first, n);
+  if (rc) return rc;
+  if (!stack) return fail(FPMB200_ERR_ARG, "stack is NULL");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const size_t per = (size_t)c->N * c->N * c->n_leds;
+  CK(cudaMemcpyAsync(c->stack + per * first, stack, sizeof(uint16_t) * per * n, cudaMemcpyHostToDevice, st));
+  c->have_stack = true;
+  return FPMB200_OK;
+}
+
+// ---- generic 2-D FFT driver (rows then columns) ------------------------------------------
+static void factorize(int n, LineFFTParams& p) {
+  p.nrad = 0;
+  while (n % 4 == 0) { p.rad[p.nrad++] = 4; n /= 4; }
+  while (n % 2 == 0) { p.rad[p.nrad++] = 2; n /= 2; }
+  while (n % 3 == 0) { p.rad[p.nrad++] = 3; n /= 3; }
+  while (n % 5 == 0) { p.rad[p.nrad++] = 5; n /= 5; }
+}
+
+template <bool INV>
+static int fft2d(fpmb200_ctx* c, float2* data, int n, const float2* tw, int batch, long long batch_stride, float scale,
+                 cudaStream_t st) {
+  constexpr int LINES = 4;
+  LineFFTParams p;
+  memset(&p, 0, sizeof p);
+  p.data = data; p.tw = tw; p.batch_stride = batch_stride; p.n = n; p.n_lines = n;
+  factorize(n, p);
+  const size_t smem = sizeof(float2) * 2 * LINES * n;
+  if (smem > (size_t)c->max_smem_optin) return fail(FPMB200_ERR_ARG, "line FFT of length %d needs %zu B shared memory", n, smem);
+  auto kern = line_fft_kernel<INV, LINES>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((n + LINES - 1) / LINES, batch);
+  p.elem_stride = 1; p.line_stride = n; p.scale = 1.f;            // rows
+  kern<<<grid, 256, smem, st>>>(p);
+  p.elem_stride = n; p.line_stride = 1; p.scale = scale;          // columns
+  kern<<<grid, 256, smem, st>>>(p);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_init_tiles(fpmb200_ctx* c, int first, int n, int init_slot, void* stream) {
+  int rc = check_range(c, first, n);
+  if (rc) return rc;
+  if (!c->have_support || !c->have_stack) return fail(FPMB200_ERR_STATE, "upload the pupil support and the stack first");
+  if (init_slot < 0 || init_slot >= c->n_leds) return fail(FPMB200_ERR_ARG, "init_led_slot %d outside [0,%d)", init_slot, c->n_leds);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const int N = c->N, L = c->L;
+  const int batch_max = (int)(c->scratch_elems / ((size_t)N * N));
+  for (int t0 = first; t0 < first + n; t0 += batch_max) {
+    const int b = (first + n - t0) < batch_max ? (first + n - t0) : batch_max;
+    init_amp_kernel<<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, N, c->n_leds, init_slot, t0);
+    c->launches++;
+    if ((rc = fft2d<false>(c, c->scratch, N, c->twN, b, (long long)N * N, 1.f, st))) return rc;
+    init_place_kernel<<<dim3(64, b), 256, 0, st>>>(c->objFc, c->pupil, c->scratch, c->support, N, L, t0);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  return FPMB200_OK;
+}
+
+template <int N, int NT, int MINB>
+static int launch_update(fpmb200_ctx* c, const UpdateParams& p, int n_blocks, cudaStream_t st) {
+  void (*k)(const UpdateParams) = nullptr;
+  constexpr bool FS = (N <= 128);
+  if (c->p_smem) k = fpm_update_kernel<N, NT, MINB, FS, true>;
+  else k = fpm_update_kernel<N, NT, MINB, FS, false>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  k<<<n_blocks, NT, c->smem_bytes, st>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  return FPMB200_OK;
+}
+
+static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
+  if (!c->have_support || !c->have_leds) return fail(FPMB200_ERR_STATE, "upload LED tables and the pupil support first");
+  UpdateParams p;
+  memset(&p, 0, sizeof p);
+  p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop;
+  p.tw = c->twN; p.field_gmem = c->field_gmem; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first;
+  p.slot_begin = slot_begin; p.n_updates = n_updates;
+  p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
+  p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi; p.bs = c->bs;
+  CK(cudaSetDevice(c->device));
+  switch (c->N) {
+    case 64: return launch_update<64, 256, 3>(c, p, n, st);
+    case 128: return launch_update<128, 512, 1>(c, p, n, st);
+    case 256: return launch_update<256, 512, 1>(c, p, n, st);
+  }
+  return fail(FPMB200_ERR_ARG, "unsupported Np");
+}
+
+extern "C" int fpmb200_run(fpmb200_ctx* c, int first, int n, int iters, void* stream) {
+  int rc = check_range(c, first, n);
+  if (rc) return rc;
+  if (iters < 0) return fail(FPMB200_ERR_ARG, "iters < 0");
+  if (iters == 0) return FPMB200_OK;
+  return run_updates(c, first, n, 0, iters * c->n_leds, stream ? (cudaStream_t)stream : c->stream);
+}
+
+extern "C" int fpmb200_step(fpmb200_ctx* c, int tile, int led_slot) {
+  int rc = check_range(c, tile, 1);
+  if (rc) return rc;
+  if (led_slot < 0 || led_slot >= c->n_leds) return fail(FPMB200_ERR_ARG, "led_slot %d outside [0,%d)", led_slot, c->n_leds);
+  if ((rc = run_updates(c, tile, 1, led_slot, 1, c->stream))) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_finalize(fpmb200_ctx* c, int first, int n, void* stream) {
+  int rc = check_range(c, first, n);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const size_t LL = (size_t)c->L * c->L;
+  shift_copy_kernel<<<dim3(64, n), 256, 0, st>>>(c->objCrop + LL * first, c->objFc + LL * first, c->L, (long long)LL, (long long)LL);
+  c->launches++;
+  return fft2d<true>(c, c->objCrop + LL * first, c->L, c->twL, n, (long long)LL, 1.0f / ((float)c->L * (float)c->L), st);
+}
+
+extern "C" int fpmb200_upload_state(fpmb200_ctx* c, int tile, const float* objF, const float* pupil) {
+  int rc = check_range(c, tile, 1);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  const size_t LL = (size_t)c->L * c->L, NN = (size_t)c->N * c->N;
+  CK(cudaDeviceSynchronize());
+  if (objF) {
+    CK(cudaMemcpy(c->scratch, objF, sizeof(float2) * LL, cudaMemcpyHostToDevice));
+    shift_copy_kernel<<<dim3(64, 1), 256, 0, c->stream>>>(c->objFc + LL * tile, c->scratch, c->L, 0, 0);
+    c->launches++;
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  if (pupil) CK(cudaMemcpy(c->pupil + NN * tile, pupil, sizeof(float2) * NN, cudaMemcpyHostToDevice));
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_download(fpmb200_ctx* c, int tile, float* objF, float* objCrop, float* pupil) {
+  int rc = check_range(c, tile, 1);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  const size_t LL = (size_t)c->L * c->L, NN = (size_t)c->N * c->N;
+  CK(cudaDeviceSynchronize());
+  if (objF) {
+    shift_copy_kernel<<<dim3(64, 1), 256, 0, c->stream>>>(c->scratch, c->objFc + LL * tile, c->L, 0, 0);
+    c->launches++;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(objF, c->scratch, sizeof(float2) * LL, cudaMemcpyDeviceToHost));
+  }
+  if (objCrop) CK(cudaMemcpy(objCrop, c->objCrop + LL * tile, sizeof(float2) * LL, cudaMemcpyDeviceToHost));
+  if (pupil) CK(cudaMemcpy(pupil, c->pupil + NN * tile, sizeof(float2) * NN, cudaMemcpyDeviceToHost));
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_download_objcrop(fpmb200_ctx* c, int first, int n, float* objCrop, void* stream) {
+  int rc = check_range(c, first, n);
+  if (rc) return rc;
+  if (!objCrop) return fail(FPMB200_ERR_ARG, "objCrop is NULL");
+  CK(cudaSetDevice(c->device));
+  const size_t LL = (size_t)c->L * c->L;
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  CK(cudaMemcpyAsync(objCrop, c->objCrop + LL * first, sizeof(float2) * LL * n, cudaMemcpyDeviceToHost, st));
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_sync(fpmb200_ctx* c) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  return FPMB200_OK;
+}
+
+extern "C" long long fpmb200_kernel_launches(const fpmb200_ctx* c) { return c ? c->launches : 0; }
+extern "C" const char* fpmb200_variant(const fpmb200_ctx* c) { return c ? c->variant : ""; }

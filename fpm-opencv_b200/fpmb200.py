@@ -1,0 +1,170 @@
+"""ctypes binding of the C ABI in include/fpmb200.h (libfpmb200.so) and include/fpmhost.h
+(libfpmhost.so).  Plumbing for tests/ and bench.py only -- the product's host side is the C++
+`fpmMain` / `runFPM` in fpm-opencv_b200/host; nothing here computes.
+
+Fails loudly (ImportError / RuntimeError) when the CUDA library is missing: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+INCLUDE_DIR = os.path.abspath(os.path.join(_HERE, "..", "include"))
+
+_lib = None
+
+
+def lib_path() -> str:
+    return os.path.join(LIB_DIR, "libfpmb200.so")
+
+
+def load():
+    """dlopen libfpmb200.so (built in-tree by `make -C fpm-opencv_b200` / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                          "there is no CPU fallback" % p)
+    L = C.CDLL(p)
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    sig = {
+        "fpmb200_last_error": (C.c_char_p, []),
+        "fpmb200_abi_version": (i, []),
+        "fpmb200_create": (i, [i, C.POINTER(vp)]),
+        "fpmb200_destroy": (None, [vp]),
+        "fpmb200_tiles_alloc": (i, [vp, i, i, i, i]),
+        "fpmb200_set_params": (i, [vp, f, f, f, i]),
+        "fpmb200_upload_leds": (i, [vp, vp, vp, i]),
+        "fpmb200_upload_pupil_support": (i, [vp, vp]),
+        "fpmb200_upload_stack": (i, [vp, i, i, vp, vp]),
+        "fpmb200_init_tiles": (i, [vp, i, i, i, vp]),
+        "fpmb200_run": (i, [vp, i, i, i, vp]),
+        "fpmb200_step": (i, [vp, i, i]),
+        "fpmb200_finalize": (i, [vp, i, i, vp]),
+        "fpmb200_upload_state": (i, [vp, i, vp, vp]),
+        "fpmb200_download": (i, [vp, i, vp, vp, vp]),
+        "fpmb200_download_objcrop": (i, [vp, i, i, vp, vp]),
+        "fpmb200_sync": (i, [vp]),
+        "fpmb200_kernel_launches": (C.c_longlong, [vp]),
+        "fpmb200_variant": (C.c_char_p, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTS = ["fpmb200_last_error", "fpmb200_abi_version", "fpmb200_create", "fpmb200_destroy",
+           "fpmb200_tiles_alloc", "fpmb200_set_params", "fpmb200_upload_leds",
+           "fpmb200_upload_pupil_support", "fpmb200_upload_stack", "fpmb200_init_tiles", "fpmb200_run",
+           "fpmb200_step", "fpmb200_finalize", "fpmb200_upload_state", "fpmb200_download",
+           "fpmb200_download_objcrop", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
+
+
+class FpmError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """Thin object wrapper: one per CUDA device, mirrors the call order runFPM() needs."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        h = C.c_void_p()
+        self._h = None
+        self._ck(self.L.fpmb200_create(device, C.byref(h)))
+        self._h = h
+        self.n_tiles = self.Np = self.Nlarge = self.n_leds = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FpmError("fpmb200 error %d: %s" % (rc, self.L.fpmb200_last_error().decode()))
+
+    def close(self):
+        if self._h is not None:
+            self.L.fpmb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tiles_alloc(self, n_tiles, Np, Nlarge, n_leds):
+        self._ck(self.L.fpmb200_tiles_alloc(self._h, n_tiles, Np, Nlarge, n_leds))
+        self.n_tiles, self.Np, self.Nlarge, self.n_leds = n_tiles, Np, Nlarge, n_leds
+
+    def set_params(self, delta1, delta2, eps, literal_scalar=1):
+        self._ck(self.L.fpmb200_set_params(self._h, float(delta1), float(delta2), float(eps), int(literal_scalar)))
+
+    def upload_leds(self, cropX, cropY):
+        cx = np.ascontiguousarray(cropX, dtype=np.int16)
+        cy = np.ascontiguousarray(cropY, dtype=np.int16)
+        self._ck(self.L.fpmb200_upload_leds(self._h, _ptr(cx), _ptr(cy), len(cx)))
+
+    def upload_pupil_support(self, mask):
+        m = np.ascontiguousarray(mask, dtype=np.float32)
+        assert m.shape == (self.Np, self.Np)
+        self._ck(self.L.fpmb200_upload_pupil_support(self._h, _ptr(m)))
+
+    def upload_stack(self, tile_first, stack, stream=None):
+        s = np.ascontiguousarray(stack, dtype=np.uint16)
+        n = s.size // (self.n_leds * self.Np * self.Np)
+        assert n * self.n_leds * self.Np * self.Np == s.size
+        self._ck(self.L.fpmb200_upload_stack(self._h, tile_first, n, _ptr(s), stream))
+        if stream is None:
+            self.sync()
+
+    def upload_stack_ptr(self, tile_first, n, host_ptr, stream=None):
+        self._ck(self.L.fpmb200_upload_stack(self._h, tile_first, n, C.c_void_p(host_ptr), stream))
+
+    def init_tiles(self, tile_first=0, n=None, init_led_slot=1, stream=None):
+        self._ck(self.L.fpmb200_init_tiles(self._h, tile_first, self.n_tiles - tile_first if n is None else n,
+                                           init_led_slot, stream))
+
+    def run(self, iters, tile_first=0, n=None, stream=None):
+        self._ck(self.L.fpmb200_run(self._h, tile_first, self.n_tiles - tile_first if n is None else n, iters, stream))
+
+    def step(self, tile, led_slot):
+        self._ck(self.L.fpmb200_step(self._h, tile, led_slot))
+
+    def finalize(self, tile_first=0, n=None, stream=None):
+        self._ck(self.L.fpmb200_finalize(self._h, tile_first, self.n_tiles - tile_first if n is None else n, stream))
+
+    def upload_state(self, tile, objF=None, pupil=None):
+        o = None if objF is None else np.ascontiguousarray(objF, dtype=np.complex64)
+        p = None if pupil is None else np.ascontiguousarray(pupil, dtype=np.complex64)
+        self._ck(self.L.fpmb200_upload_state(self._h, tile, _ptr(o), _ptr(p)))
+
+    def download(self, tile, objF=True, objCrop=True, pupil=True):
+        o = np.empty((self.Nlarge, self.Nlarge), np.complex64) if objF else None
+        c = np.empty((self.Nlarge, self.Nlarge), np.complex64) if objCrop else None
+        p = np.empty((self.Np, self.Np), np.complex64) if pupil else None
+        self._ck(self.L.fpmb200_download(self._h, tile, _ptr(o), _ptr(c), _ptr(p)))
+        return o, c, p
+
+    def download_objcrop_ptr(self, tile_first, n, host_ptr, stream=None):
+        self._ck(self.L.fpmb200_download_objcrop(self._h, tile_first, n, C.c_void_p(host_ptr), stream))
+
+    def sync(self):
+        self._ck(self.L.fpmb200_sync(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.L.fpmb200_kernel_launches(self._h))
+
+    @property
+    def variant(self) -> str:
+        return self.L.fpmb200_variant(self._h).decode()

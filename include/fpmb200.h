@@ -1,0 +1,102 @@
+/* fpmb200.h -- C ABI of the B200-native FPM reconstruction path (libfpmb200.so).
+ *
+ * The reference (Xiongda337/fpm-OpenCV) has no plugin/FFI interface: its boundary is the
+ * executable `fpmMain <dataset.json> <itrCount>` and two C++ functions,
+ *     int16_t loadFPMDataset(FPM_Dataset*);   fpmMain.h:118
+ *     void    runFPM(FPM_Dataset*);           fpmMain.h:119
+ * This header is what a maintainer's `runFPM()` binds instead of the cv::UMat/cvComplex
+ * call sequence of fpmMain.cpp:274-498 (see INTEGRATION.md for the stub).  Plain C:
+ * opaque handle, plain pointers and sizes, int status codes, no exceptions, no torch/OpenCV
+ * types.  All host pointers are caller-owned; calls on one context are not re-entrant
+ * (the reference is single-threaded, fpmMain.cpp:29-33); one context per CUDA device.
+ *
+ * Conventions
+ *   Np      low-res tile edge (`FPM_Dataset::Np`, fpmMain.h:66), 64 | 128 | 256
+ *   Nlarge  high-res edge (`Nlarge == Mlarge`, fpmMain.h:70-71, fpmMain.cpp:564-565), multiple of 64
+ *   objF    [Nlarge][Nlarge][2] float, DC-at-corner like `FPM_Dataset::objF` (fpmMain.h:92)
+ *   objCrop [Nlarge][Nlarge][2] float = IDFT_scaled(objF) (`FPM_Dataset::objCrop`, fpmMain.cpp:481)
+ *   pupil   [Np][Np][2] float, DC-at-corner like `FPM_Dataset::pupil` (fpmMain.h:94)
+ *   stack   [n_leds][Np][Np] uint16 in UPDATE ORDER (`sortedIndicies`, fpmMain.cpp:246-258,350):
+ *           slot k holds `imageStack[sortedIndicies[k]].Image` after loader preprocessing
+ *   led tables: `cropXStart/cropYStart` (fpmMain.h:37-39) per slot, same order
+ * There is no CPU fallback: every entry point fails with FPMB200_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef FPMB200_H
+#define FPMB200_H 1
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fpmb200_ctx fpmb200_ctx;
+
+enum {
+  FPMB200_OK = 0,
+  FPMB200_ERR_ARG = -1,      /* bad argument / unsupported size */
+  FPMB200_ERR_CUDA = -2,     /* CUDA runtime error (message in fpmb200_last_error) */
+  FPMB200_ERR_STATE = -3     /* call order violated (e.g. run before upload) */
+};
+
+/* Last error message of the calling thread ("" if none). */
+const char* fpmb200_last_error(void);
+/* ABI version of this header (bumped on incompatible change). */
+int fpmb200_abi_version(void);
+
+/* One context per CUDA device ordinal (use_gpu.sh: OPENCV_OPENCL_DEVICE=GPU:<n>). */
+int  fpmb200_create(int device, fpmb200_ctx** out);
+void fpmb200_destroy(fpmb200_ctx* ctx);
+
+/* Allocates device state for `n_tiles` independent tiles that share one LED geometry.
+ * Replaces the UMat allocations of runFPM (fpmMain.cpp:282-297,330-332). */
+int fpmb200_tiles_alloc(fpmb200_ctx* ctx, int n_tiles, int Np, int Nlarge, int n_leds);
+
+/* delta1/delta2/eps of FPM_Dataset (fpmMain.h:88-89,99).  `literal_scalar` selects how the
+ * float scalars of cv::add (fpmMain.cpp:390,417,469) broadcast: 1 = to both channels (what the
+ * shipped source does against stock OpenCV: complex denominators), 0 = real part only. */
+int fpmb200_set_params(fpmb200_ctx* ctx, float delta1, float delta2, float eps, int literal_scalar);
+
+/* Per-slot crop origins (fpmMain.cpp:157-165), already in update order.  Each must satisfy
+ * 0 <= start <= Nlarge-Np. */
+int fpmb200_upload_leds(fpmb200_ctx* ctx, const int16_t* cropXStart, const int16_t* cropYStart, int n_leds);
+
+/* `FPM_Dataset::pupilSupport` real plane, [Np][Np], DC-at-corner (fpmMain.cpp:304-313). */
+int fpmb200_upload_pupil_support(fpmb200_ctx* ctx, const float* mask);
+
+/* Copies the intensity stacks of tiles [tile_first, tile_first+n) host->device on `stream`
+ * (cudaStream_t or NULL = the context's stream).  Asynchronous when `stack` is pinned. */
+int fpmb200_upload_stack(fpmb200_ctx* ctx, int tile_first, int n, const uint16_t* stack, void* stream);
+
+/* Pupil + spectrum initialisation of fpmMain.cpp:301-343 for tiles [tile_first, tile_first+n):
+ * pupil = support, objF = fftShift-placed FFT of sqrt(image of slot `init_led_slot`) filtered by
+ * the support.  The reference uses slot 1 (`sortedIndicies.at(1)`, fpmMain.cpp:319). */
+int fpmb200_init_tiles(fpmb200_ctx* ctx, int tile_first, int n, int init_led_slot, void* stream);
+
+/* `iters` passes of the inner loops fpmMain.cpp:345-476 over all LED slots, sequential order
+ * preserved, for tiles [tile_first, tile_first+n).  Asynchronous on `stream`. */
+int fpmb200_run(fpmb200_ctx* ctx, int tile_first, int n, int iters, void* stream);
+
+/* One sub-aperture update (fpmMain.cpp:350-475) of one tile; for per-step parity. */
+int fpmb200_step(fpmb200_ctx* ctx, int tile, int led_slot);
+
+/* objCrop = IDFT_scaled(objF) (fpmMain.cpp:481) for tiles [tile_first, tile_first+n). */
+int fpmb200_finalize(fpmb200_ctx* ctx, int tile_first, int n, void* stream);
+
+/* State injection / extraction (any pointer may be NULL).  Synchronous. */
+int fpmb200_upload_state(fpmb200_ctx* ctx, int tile, const float* objF, const float* pupil);
+int fpmb200_download(fpmb200_ctx* ctx, int tile, float* objF, float* objCrop, float* pupil);
+/* Asynchronous gather of objCrop of tiles [tile_first,tile_first+n) into pinned host memory. */
+int fpmb200_download_objcrop(fpmb200_ctx* ctx, int tile_first, int n, float* objCrop, void* stream);
+
+int fpmb200_sync(fpmb200_ctx* ctx);
+
+/* Introspection: kernels launched by this context so far, and the name/shape of the update
+ * kernel variant selected for the current allocation (for logs and bench.py). */
+long long   fpmb200_kernel_launches(const fpmb200_ctx* ctx);
+const char* fpmb200_variant(const fpmb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPMB200_H */
