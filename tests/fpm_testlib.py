@@ -1,0 +1,71 @@
+"""Shared helpers for the tests: golden geometry, synthetic stacks, oracle runs."""
+import functools
+import json
+import os
+
+import numpy as np
+
+import fpm_oracle as orc
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CONFIGS = os.path.join(ROOT, "configs")
+
+ALL_CFGS = ["cfg1_mono_np64", "cfg2_fLEDc_np128", "cfg3_cellScope_np256", "cfg3b_cellScope_np64",
+            "cfg4_dogStomach_np128", "cfg4s_dogStomach_np200", "cfg5_cellscope2_np128",
+            "cfg5b_cellscope2_np256", "cfg6_mono_dome_np64"]
+QUIRKS = ["quirks_rot", "quirks_flipxy"]
+
+
+def golden(name):
+    return json.load(open(os.path.join(GOLD, "geometry_%s.json" % name)))
+
+
+def embedded_path(name):
+    return os.path.join(GOLD, (name + ".json") if name.startswith("quirks") else (name + ".embedded.json"))
+
+
+class Case:
+    """One synthetic single-tile problem derived from a golden geometry."""
+
+    def __init__(self, name, seed, n_leds=None):
+        g = golden(name)
+        j = orc.load_json_lenient(embedded_path(name))
+        self.name, self.cfg = name, orc.config_from_json(j)
+        byn = {l["n"]: l for l in g["leds"]}
+        order = g["order"] if n_leds is None else g["order"][:n_leds]
+        self.order = order
+        self.cx = np.array([byn[n]["cropX"] for n in order], np.int16)
+        self.cy = np.array([byn[n]["cropY"] for n in order], np.int16)
+        c = self.cfg
+        self.N, self.L, self.r = c.Np, c.Nlarge, c.naRadius
+        self.stack = orc.synth_stack(c.Np, c.Nlarge, c.naRadius, self.cx, self.cy, seed)
+        self.support = orc.pupil_support(c.Np, c.naRadius)
+
+    def oracle_run(self, iters, kappa=1, trace=None):
+        c = self.cfg
+        return orc.run(self.stack, self.cx, self.cy, self.L, self.r, c.delta1, c.delta2, c.eps, iters, kappa, trace=trace)
+
+    def make_ctx(self, n_tiles=1, kappa=1, support=None, device=0):
+        import fpmb200
+        c = self.cfg
+        ctx = fpmb200.Context(device)
+        ctx.tiles_alloc(n_tiles, self.N, self.L, len(self.cx))
+        ctx.set_params(c.delta1, c.delta2, c.eps, kappa)
+        ctx.upload_leds(self.cx, self.cy)
+        ctx.upload_pupil_support(self.support if support is None else support)
+        for t in range(n_tiles):
+            ctx.upload_stack(t, self.stack)
+        ctx.init_tiles()
+        ctx.sync()
+        return ctx
+
+
+@functools.lru_cache(maxsize=16)
+def case(name, seed=1234, n_leds=None):
+    return Case(name, seed, n_leds)
+
+
+def corner(objFc):
+    """centred spectrum -> the reference's DC-at-corner objF"""
+    return np.fft.ifftshift(objFc)

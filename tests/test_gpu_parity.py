@@ -1,0 +1,269 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI of include/fpmb200.h,
+against the float64 oracle on the same seeded synthetic stacks.
+
+Tolerances (BASELINE.json north_star): relative L2 <= 1e-5 per update step, <= 1e-3 after the full
+iteration count, on objF / pupil / objCrop.  kappa = 1 (literal OpenCV scalar broadcast, SURVEY 8c
+R5) unless stated.  Integer inputs (crop tables, LED order) come from the golden geometry, which the
+CPU tests pin bit-exactly."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fpm_oracle as orc
+import fpm_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-5
+FULL_TOL = 1e-3
+
+
+def _need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.fixture(autouse=True)
+def _gpu():
+    _need_gpu()
+
+
+def compare(ctx, st, tile=0, tol=FULL_TOL, crop=True):
+    gF, gC, gP = ctx.download(tile, objCrop=crop)
+    eF, eP = orc.rel_l2(gF, T.corner(st.objFc)), orc.rel_l2(gP, st.P)
+    assert np.isfinite(gF).all() and np.isfinite(gP).all()
+    assert eF < tol and eP < tol, (eF, eP)
+    if crop:
+        eC = orc.rel_l2(gC, orc.obj_crop(st))
+        assert eC < tol, eC
+        # amplitude and phase separately (phase where amplitude is significant)
+        oc = orc.obj_crop(st)
+        amp_err = orc.rel_l2(np.abs(gC), np.abs(oc))
+        m = np.abs(oc) > 1e-3 * np.abs(oc).max()
+        ph_err = np.abs(np.angle(gC[m] * np.conj(oc[m]))).max()
+        assert amp_err < tol and ph_err < tol, (amp_err, ph_err)
+    return eF, eP
+
+
+# ---- initialisation (fpmMain.cpp:301-343) ----------------------------------------------------
+@pytest.mark.parametrize("name", ["cfg1_mono_np64", "cfg2_fLEDc_np128", "cfg5_cellscope2_np128"])
+def test_init_state(name):
+    c = T.case(name)
+    ctx = c.make_ctx()
+    st = orc.init_state(c.stack, c.L, c.r)
+    gF, _, gP = ctx.download(0, objCrop=False)
+    assert np.array_equal(gP, st.P.astype(np.complex64))          # pupil = support, exactly
+    assert orc.rel_l2(gF, T.corner(st.objFc)) < 1e-6
+    ctx.close()
+
+
+# ---- per-step parity: every update starts from the oracle's float64 state ---------------------
+@pytest.mark.parametrize("name,n_steps", [("cfg1_mono_np64", 117), ("cfg2_fLEDc_np128", 89), ("cfg3b_cellScope_np64", 60),
+                                          ("cfg5_cellscope2_np128", 40)])
+@pytest.mark.parametrize("kappa", [1, 0])
+def test_per_step_parity(name, n_steps, kappa):
+    c = T.case(name)
+    ctx = c.make_ctx(kappa=kappa)
+    st = orc.init_state(c.stack, c.L, c.r)
+    # warm the oracle state up so that the pupil is not the trivial binary mask
+    for k in range(len(c.cx)):
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, kappa)
+    worst = 0.0
+    for k in range(min(n_steps, len(c.cx))):
+        ctx.upload_state(0, T.corner(st.objFc), st.P)
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, kappa)
+        ctx.step(0, k)
+        worst = max(worst, *compare(ctx, st, tol=STEP_TOL, crop=False))
+    print("%s kappa=%d worst per-step rel-L2 %.2e" % (name, kappa, worst))
+    ctx.close()
+
+
+# ---- full runs at the BASELINE configurations --------------------------------------------------
+@pytest.mark.parametrize("name,iters", [("cfg1_mono_np64", 10), ("cfg2_fLEDc_np128", 10), ("cfg3b_cellScope_np64", 3),
+                                        ("cfg4_dogStomach_np128", 10), ("cfg5_cellscope2_np128", 4),
+                                        ("cfg6_mono_dome_np64", 3)])
+def test_full_run_parity(name, iters):
+    c = T.case(name)
+    ctx = c.make_ctx()
+    ctx.run(iters)
+    ctx.finalize()
+    st = c.oracle_run(iters)
+    e = compare(ctx, st)
+    print("%s %d iterations x %d LEDs: rel-L2 objF %.2e pupil %.2e [%s]" % (name, iters, len(c.cx), e[0], e[1], ctx.variant))
+    ctx.close()
+
+
+def test_full_run_parity_kappa0():
+    c = T.case("cfg1_mono_np64")
+    ctx = c.make_ctx(kappa=0)
+    ctx.run(5)
+    ctx.finalize()
+    compare(ctx, c.oracle_run(5, kappa=0))
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,n_leds,iters", [("cfg5b_cellscope2_np256", 40, 2), ("cfg3_cellScope_np256", 24, 1)])
+def test_np256_tiles(name, n_leds, iters):
+    """Np=256 (field does not fit one SM's shared memory; Nlarge 1024 / 1536 = 3*2^9)."""
+    c = T.case(name, n_leds=n_leds)
+    ctx = c.make_ctx()
+    ctx.run(iters)
+    ctx.finalize()
+    e = compare(ctx, c.oracle_run(iters))
+    print(name, e, ctx.variant)
+    ctx.close()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(T.GOLD, "loop_*.npz"))))
+def test_against_committed_opencv_fixtures(path):
+    """States produced by OpenCV's own cv::dft/arithmetic op sequence (oracle/cv2_mirror.py)."""
+    z = np.load(path)
+    c = T.Case(str(z["name"]), int(z["seed"]), int(z["n_leds"]))
+    ctx = c.make_ctx(kappa=int(z["kappa"]))
+    ctx.run(int(z["iters"]))
+    ctx.finalize()
+    gF, gC, gP = ctx.download(0)
+    assert orc.rel_l2(gF, z["objF"]) < 1e-5 and orc.rel_l2(gP, z["pupil"]) < 1e-5 and orc.rel_l2(gC, z["objCrop"]) < 1e-5
+    ctx.close()
+
+
+# ---- structure / edge cases ----------------------------------------------------------------------
+def test_dense_support_uses_general_path():
+    """A support mask covering the whole window: no bbox pruning, pupil kept in global memory at
+    Np=128 (does not fit next to the field).  Same arithmetic as the oracle with S = 1."""
+    for name, n_leds in (("cfg1_mono_np64", 20), ("cfg2_fLEDc_np128", 12)):
+        c = T.Case(name, 3, n_leds)
+        full = np.ones((c.N, c.N), np.float32)
+        ctx = c.make_ctx(support=full)
+        assert "bbox=[-%d..%d]" % (c.N // 2, c.N // 2 - 1) in ctx.variant
+        st = orc.init_state(c.stack, c.L, c.r)
+        st.S = full.astype(np.float64)
+        ctx.upload_state(0, T.corner(st.objFc), st.P)
+        for it in range(2):
+            for k in range(n_leds):
+                orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+        ctx.run(2)
+        ctx.finalize()
+        compare(ctx, st)
+        ctx.close()
+
+
+def test_asymmetric_support_bbox():
+    """An off-centre elliptical support exercises the wrapped bbox arithmetic."""
+    c = T.Case("cfg1_mono_np64", 4, 16)
+    N = c.N
+    y, x = np.mgrid[0:N, 0:N]
+    yw, xw = np.where(y < N // 2, y, y - N), np.where(x < N // 2, x, x - N)
+    S = ((((xw - 3) / 14.0) ** 2 + ((yw + 5) / 9.0) ** 2) <= 1).astype(np.float32)
+    ctx = c.make_ctx(support=S)
+    st = orc.State(orc.init_state(c.stack, c.L, c.r).objFc, S.astype(np.complex128), S.astype(np.float64))
+    ctx.upload_state(0, T.corner(st.objFc), st.P)
+    for k in range(16):
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+    ctx.run(1)
+    ctx.finalize()
+    compare(ctx, st)
+    ctx.close()
+
+
+def test_windows_touching_the_spectrum_border():
+    """Crop origins 0 and Nlarge-Np (the legal extremes, fpmMain.cpp:157-165)."""
+    c = T.Case("cfg1_mono_np64", 5, 8)
+    c.cx = np.array([0, c.L - c.N, 0, c.L - c.N, 96, 7, c.L - c.N - 1, 1], np.int16)
+    c.cy = np.array([0, 0, c.L - c.N, c.L - c.N, 96, c.L - c.N - 3, 5, 1], np.int16)
+    ctx = c.make_ctx()
+    ctx.run(2)
+    ctx.finalize()
+    compare(ctx, c.oracle_run(2))
+    ctx.close()
+
+
+def test_steps_equal_run_bitwise():
+    """n_leds single-update launches == one persistent launch, bit for bit (state round-trips exactly)."""
+    c = T.Case("cfg1_mono_np64", 6, 30)
+    a, b = c.make_ctx(), c.make_ctx()
+    a.run(1)
+    for k in range(30):
+        b.step(0, k)
+    for x, y in zip(a.download(0, objCrop=False), b.download(0, objCrop=False)):
+        if x is not None:
+            assert np.array_equal(x, y)
+    a.close(), b.close()
+
+
+def test_tiles_are_independent_and_deterministic():
+    """Many tiles in one launch (more CTAs than fit at once): identical inputs give identical bits in
+    every slot, different inputs do not interfere -- the property the multi-GPU sharding relies on."""
+    import fpmb200
+    c1, c2 = T.Case("cfg2_fLEDc_np128", 21, 10), T.Case("cfg2_fLEDc_np128", 22, 10)
+    n_tiles = 300
+    ctx = fpmb200.Context(0)
+    ctx.tiles_alloc(n_tiles, c1.N, c1.L, 10)
+    ctx.set_params(c1.cfg.delta1, c1.cfg.delta2, c1.cfg.eps, 1)
+    ctx.upload_leds(c1.cx, c1.cy)
+    ctx.upload_pupil_support(c1.support)
+    for t in range(n_tiles):
+        ctx.upload_stack(t, c2.stack if t % 7 == 3 else c1.stack)
+    ctx.init_tiles()
+    ctx.run(2)
+    ctx.finalize()
+    ref1, ref2 = ctx.download(0), ctx.download(3)
+    for t in (1, 2, 147, 148, 149, 295, 299, 10, 17, 290):
+        got = ctx.download(t)
+        want = ref2 if t % 7 == 3 else ref1
+        assert all(np.array_equal(g, w) for g, w in zip(got, want)), t
+    compare(ctx, c1.oracle_run(2), tile=299)
+    compare(ctx, c2.oracle_run(2), tile=290)
+    ctx.close()
+
+
+def test_argument_errors_are_reported_not_masked():
+    import fpmb200
+    ctx = fpmb200.Context(0)
+    with pytest.raises(fpmb200.FpmError):
+        ctx.tiles_alloc(1, 100, 400, 10)            # unsupported tile edge
+    with pytest.raises(fpmb200.FpmError):
+        ctx.tiles_alloc(1, 64, 448, 10)             # 448 = 2^6 * 7: prime factor 7
+    ctx.tiles_alloc(1, 64, 256, 4)
+    with pytest.raises(fpmb200.FpmError):
+        ctx.upload_leds([0, 0, 0, 193], [0, 0, 0, 0])   # window would leave the spectrum
+    with pytest.raises(fpmb200.FpmError):
+        ctx.run(1)                                   # nothing uploaded yet
+    with pytest.raises(fpmb200.FpmError):
+        fpmb200.Context(1 << 20)
+    ctx.close()
+
+
+def test_fpmMain_end_to_end(tmp_path):
+    """The reference's entry point on a directory of TIFFs: `fpmMain <dataset.json> <itrCount>`."""
+    import json
+    from test_host import write_tiff16
+    c = T.Case("cfg1_mono_np64", 9, 20)
+    j = json.load(open(os.path.join(T.GOLD, "cfg1_mono_np64.embedded.json")))
+    root = tmp_path / "frames"
+    root.mkdir()
+    j.update(datasetRoot=str(root) + "/", cropX=5, cropY=7, bk1cropX=0, bk1cropY=0, bk2cropX=0, bk2cropY=0, bgThresh=0)
+    (tmp_path / "d.json").write_text(json.dumps(j))
+    for k, n in enumerate(c.order):
+        fr = np.zeros((80, 90), np.uint16)
+        fr[7:7 + 64, 5:5 + 64] = c.stack[k]
+        write_tiff16(str(root / ("iLED_%04d.tif" % n)), fr)
+    out = tmp_path / "out"
+    out.mkdir()
+    exe = os.path.join(T.ROOT, "fpm-opencv_b200", "bin", "fpmMain")
+    env = dict(os.environ, OPENCV_OPENCL_DEVICE="GPU:0")
+    r = subprocess.run([exe, str(tmp_path / "d.json"), "3", str(out)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for line in ("Loading Images...", "resImprovementFactor: 4", "Iteration 3 Completed (Time:", "FP Processing Completed (Time:"):
+        assert line in r.stdout
+    assert r.stdout.count("Loaded: iLED_") == 20
+    # result files: amplitude of the object against the oracle
+    import fpmhost  # noqa: F401
+    data = open(out / "object_amp.tif", "rb").read()
+    amp = np.frombuffer(data[8:8 + 4 * c.L * c.L], np.float32).reshape(c.L, c.L)
+    st = c.oracle_run(3)
+    assert orc.rel_l2(amp, np.abs(orc.obj_crop(st))) < FULL_TOL
