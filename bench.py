@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- sub-aperture updates/s of the FPM reconstruction loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[3] geometry, `dataset_dogStomach.json` optics with
+128x128 tiles (Nlarge 384, 157 LEDs in the reference's NA order, 10 iterations, EPRY pupil update on),
+`--tiles-per-gpu` independent tiles per GPU (default 592 = 4 waves of 148 CTAs).  One "step" = one
+complete reconstruction of every tile of the rank: spectrum/pupil initialisation, iterations x LEDs
+fused updates, final Nlarge x Nlarge inverse FFT.  Tiles are sharded over ranks with no data-path
+collective (weak scaling: per-GPU work fixed); the only communication is the timing reduction and,
+in the full-FOV leg, the final gather.
+
+`value`  : updates/s with the stacks resident in HBM, CUDA events on the launching stream, max over ranks.
+`e2e`    : same metric through the C ABI from pinned HOST buffers: H2D of every stack and D2H of every
+           objCrop inside the timed region (chunked, copy/compute overlapped on three streams).
+`roofline`: the fused update kernel against the measured HBM peak with SURVEY 8d's algorithmic bytes
+           (18*Np^2 per update); `roofline_fp32` adds the FP32 view the north star asks for.
+`--impl reference`: the reference's CPU path (1:1 OpenCV op-sequence mirror, oracle/cv2_mirror.py --
+           the reference binary itself cannot be built here) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(ROOT, "fpm-opencv_b200")]
+
+import numpy as np  # noqa: E402
+
+CFG_JSON = os.path.join(ROOT, "configs", "cfg4_dogStomach_np128.json")
+WORKLOAD = "dogStomach optics (configs[3]), 128x128 tiles, Nlarge 384, 157 LEDs, {iters} iterations, {tiles} tiles/GPU"
+METRIC = "sub-aperture updates/sec (aggregate over GPUs)"
+UNIT = "updates/s"
+FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12        # #SM * 128 lanes * 2 * f_max
+
+
+def flops_per_update(N):
+    return 20.0 * N * N * np.log2(N) + 86.0 * N * N
+
+
+def bytes_per_update(N):            # window read + write (fp32 complex) + uint16 intensity
+    return 18.0 * N * N
+
+
+def geometry():
+    """LED tables through the product's own host layer (C++ libfpmhost, not the oracle)."""
+    import fpmhost
+    ds = fpmhost.Dataset(CFG_JSON, 10)
+    s = ds.scalars
+    n = ds.geometry(1, min(293, s.ledCount))
+    cx, cy = ds.crop_tables()
+    return dict(N=s.Np, L=s.Nlarge, r=s.naRadius, n_leds=n, cx=cx, cy=cy, delta1=s.delta1, delta2=s.delta2, eps=s.eps,
+                support=fpmhost.pupil_support(s.Np, s.naRadius))
+
+
+def distinct_stacks(g, k, seed0=4000):
+    import synth
+    return [synth.synth_stack(g["N"], g["L"], g["r"], g["cx"], g["cy"], seed0 + i) for i in range(k)]
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.sm_max, self._stop = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import fpmb200
+    import sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = geometry()
+    N, L, n_leds, iters = g["N"], g["L"], g["n_leds"], args.iters
+    tiles = args.tiles_per_gpu
+    ctx = fpmb200.Context(local)
+    ctx.tiles_alloc(tiles, N, L, n_leds)
+    ctx.set_params(g["delta1"], g["delta2"], g["eps"], 1)
+    ctx.upload_leds(g["cx"], g["cy"])
+    ctx.upload_pupil_support(g["support"])
+
+    # ---- synthetic input: 8 distinct seeded tiles replicated into a pinned host buffer ----
+    per_tile = n_leds * N * N
+    host_in = torch.empty((tiles, per_tile), dtype=torch.int16).pin_memory()
+    distinct = distinct_stacks(g, 8, 4000 + 100 * rank)
+    hin = host_in.numpy().view(np.uint16)
+    for t in range(tiles):
+        hin[t] = distinct[t % len(distinct)].reshape(-1)
+    host_out = torch.empty((tiles, L * L * 2), dtype=torch.float32).pin_memory()
+    ctx.upload_stack_ptr(0, tiles, host_in.data_ptr(), None)
+    ctx.sync()
+
+    main = torch.cuda.current_stream()
+    sp = main.cuda_stream
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(k_ev=None):
+        ctx.init_tiles(0, tiles, 1, sp)
+        if k_ev:
+            k_ev[0].record(main)
+        ctx.run(iters, 0, tiles, sp)
+        if k_ev:
+            k_ev[1].record(main)
+        ctx.finalize(0, tiles, sp)
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.kernel_launches
+    e0, e1 = ev(), ev()
+    kev = [(ev(), ev()) for _ in range(args.steps)]
+    e0.record(main)
+    for s in range(args.steps):
+        step_resident(kev[s])
+    e1.record(main)
+    barrier()
+    clocks = sampler.finish()
+    launches = ctx.kernel_launches - l0
+    ms = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    ms_max = sharding.max_over_ranks(ms, "cuda")
+    updates_per_step_rank = tiles * n_leds * iters
+    value = world * updates_per_step_rank * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: pinned host -> device -> pinned host, chunked and overlapped on three streams ----
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    chunk = args.chunk
+    n_chunks = (tiles + chunk - 1) // chunk
+    in_bytes, out_bytes = per_tile * 2, L * L * 8
+
+    def step_e2e():
+        start = ev()
+        start.record(main)
+        s_in.wait_event(start)
+        done = []
+        for c in range(n_chunks):
+            a = c * chunk
+            n = min(chunk, tiles - a)
+            ctx.upload_stack_ptr(a, n, host_in.data_ptr() + a * in_bytes, s_in.cuda_stream)
+            e_in = torch.cuda.Event()
+            e_in.record(s_in)
+            main.wait_event(e_in)
+            ctx.init_tiles(a, n, 1, sp)
+            ctx.run(iters, a, n, sp)
+            ctx.finalize(a, n, sp)
+            e_c = torch.cuda.Event()
+            e_c.record(main)
+            s_out.wait_event(e_c)
+            ctx.download_objcrop_ptr(a, n, host_out.data_ptr() + a * out_bytes, s_out.cuda_stream)
+            e_o = torch.cuda.Event()
+            e_o.record(s_out)
+            done.append(e_o)
+        for e_o in done:
+            main.wait_event(e_o)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e2, e3 = ev(), ev()
+    e2.record(main)
+    for _ in range(args.steps):
+        step_e2e()
+    e3.record(main)
+    barrier()
+    ms_e2e = sharding.max_over_ranks(e2.elapsed_time(e3), "cuda")
+    e2e_value = world * updates_per_step_rank * args.steps / (ms_e2e * 1e-3)
+    checksum = float(np.abs(host_out.numpy()[:: max(1, tiles // 8), :4096]).sum())
+
+    # ---- full-FOV leg (strong scaling): BASELINE configs[3] frame 2560x2160 -> 20x16 = 320 tiles
+    #      sharded over the ranks, final gather of objCrop to rank 0 ----
+    fov_tiles = len(sharding.tile_grid(2560, 2160, N))
+    a, b = sharding.shard_range(fov_tiles, rank, world)
+    nl = min(b - a, tiles)
+    barrier()
+    f0, f1 = ev(), ev()
+    f0.record(main)
+    if nl:
+        ctx.init_tiles(0, nl, 1, sp)
+        ctx.run(iters, 0, nl, sp)
+        ctx.finalize(0, nl, sp)
+    f1.record(main)
+    torch.cuda.synchronize()
+    t_g = time.perf_counter()
+    if world > 1:
+        dev_out = ctx.objcrop_tensor(0, nl) if nl else torch.empty((0, L * L * 2), dtype=torch.float32, device="cuda")
+        full = sharding.gather_tiles(dev_out, fov_tiles, rank, world)     # NCCL send/recv -> rank 0
+        torch.cuda.synchronize()
+        del full
+    gather_s = time.perf_counter() - t_g
+    fov_ms = sharding.max_over_ranks(f0.elapsed_time(f1), "cuda")
+    gather_s = sharding.max_over_ranks(gather_s, "cuda")
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        upd_per_launch = tiles * n_leds * iters
+        ach_gbs = bytes_per_update(N) * upd_per_launch / (kernel_ms * 1e-3) / 1e9
+        ach_tf = flops_per_update(N) * upd_per_launch / (kernel_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (complex64 field, uint16 intensities)", "data": "synthetic (8 seeded tiles/rank replicated; forward model of the reference)",
+            "config": {"workload": WORKLOAD.format(iters=iters, tiles=tiles), "tiles_per_gpu": tiles, "Np": N, "Nlarge": L,
+                       "n_leds": n_leds, "iterations": iters, "kappa": 1, "parallelism": "tiles sharded, no collective",
+                       "l2": "inputs larger than L2 (%.1f GB of stacks + %.1f GB of spectra per GPU)" % (
+                           tiles * in_bytes / 1e9, tiles * out_bytes / 1e9),
+                       "kernel": ctx.variant},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tiles * in_bytes * world,
+                    "d2h_bytes_per_step": tiles * out_bytes * world, "ms_per_step": ms_e2e / args.steps,
+                    "chunk_tiles": chunk, "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": None, "kernel": "fpm_update_kernel", "kernel_ms_per_launch": kernel_ms,
+                         "algorithmic_bytes_per_update": bytes_per_update(N), "updates_per_launch": upd_per_launch,
+                         "peak_source": peak_src},
+            "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
+                              "frac": ach_tf / FP32_PEAK_TFLOPS_NOMINAL, "flops_per_update": flops_per_update(N),
+                              "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (SURVEY 8d)"},
+            "full_fov": {"frame": "2560x2160", "tiles": fov_tiles, "recon_ms": fov_ms, "gather_s": gather_s,
+                         "updates_per_s": fov_tiles * n_leds * iters / (fov_ms * 1e-3), "scaling": "strong"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single(g, distinct[0], iters)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_single(g, stack, iters, budget_s=20.0):
+    """Oracle port (OpenCV op-sequence mirror) on ONE host core, bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cv2
+    import cv2_mirror
+    cv2.setNumThreads(1)
+    m = cv2_mirror.Mirror(stack, g["cx"], g["cy"], g["L"], g["r"], g["delta1"], g["delta2"], g["eps"], 1)
+    t0 = time.perf_counter()
+    n = 0
+    while n < iters * g["n_leds"] and time.perf_counter() - t0 < budget_s:
+        m.update(n % g["n_leds"])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "1 tile, %d sequential updates of the same stack (oracle/cv2_mirror.py: cv::dft float64 op sequence of fpmMain.cpp:345-482)" % n}
+
+
+def _ref_worker(a):
+    stack, g, n_updates = a
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cv2
+    import cv2_mirror
+    cv2.setNumThreads(1)
+    m = cv2_mirror.Mirror(stack, g["cx"], g["cy"], g["L"], g["r"], g["delta1"], g["delta2"], g["eps"], 1)
+    for k in range(n_updates):
+        m.update(k % g["n_leds"])
+    return float(np.abs(m.pupil).sum())
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path, all host cores, one tile per
+    worker process (tiles are independent).  Under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import multiprocessing as mp
+    g = geometry()
+    cores = os.cpu_count() or 1
+    stacks = distinct_stacks(g, min(cores, 8))
+    n_updates = args.ref_updates
+    jobs = [(stacks[i % len(stacks)], g, n_updates) for i in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_worker, [(s, g, max(4, n_updates // 8)) for s, _, _ in jobs])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_worker, jobs)
+        dt = time.perf_counter() - t0
+    value = cores * n_updates * args.steps / dt
+    sample = "%d tiles in parallel (one per core), %d sequential updates each per step" % (cores, n_updates)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (CV_64FC2, uint16 intensities)", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(iters=args.iters, tiles=args.tiles_per_gpu), "Np": g["N"], "Nlarge": g["L"],
+                       "n_leds": g["n_leds"], "kappa": 1, "host_cores": cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tiles-per-gpu", type=int, default=592)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--chunk", type=int, default=148)
+    ap.add_argument("--ref-updates", type=int, default=157)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: note: fewer than 3 warm-up steps requested", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,15 @@ extern "C" int fpmb200_create(int device, fpmb200_ctx** out) {
   return FPMB200_OK;
 }
 
+// Every copy / memset goes through the context's own (non-blocking) stream: a plain cudaMemcpy from
+// pageable memory may return before its DMA has landed, and the legacy stream is not ordered with
+// a cudaStreamNonBlocking stream -- kernels launched next could read stale data.
+static cudaError_t copy_sync(fpmb200_ctx* c, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, c->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(c->stream);
+}
+
 static void free_tiles(fpmb200_ctx* c) {
   cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->support);
   cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch);
@@ -103,13 +112,13 @@ extern "C" void fpmb200_destroy(fpmb200_ctx* c) {
   delete c;
 }
 
-static int upload_twiddles(float2* dst, int n) {
+static int upload_twiddles(fpmb200_ctx* c, float2* dst, int n) {
   std::vector<float2> h(n);
   for (int k = 0; k < n; ++k) {
     double a = -2.0 * M_PI * (double)k / (double)n;
     h[k] = make_float2((float)cos(a), (float)sin(a));
   }
-  CK(cudaMemcpy(dst, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+  CK(copy_sync(c, dst, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
   return FPMB200_OK;
 }
 
@@ -139,12 +148,14 @@ extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlar
   CK(cudaMalloc(&c->twL, sizeof(float2) * Nlarge));
   c->scratch_elems = LL > NN * 64 ? LL : NN * 64;
   CK(cudaMalloc(&c->scratch, sizeof(float2) * c->scratch_elems));
-  CK(cudaMemset(c->objFc, 0, sizeof(float2) * LL * n_tiles));
-  CK(cudaMemset(c->objCrop, 0, sizeof(float2) * LL * n_tiles));
-  CK(cudaMemset(c->pupil, 0, sizeof(float2) * NN * n_tiles));
+  CK(cudaMemsetAsync(c->objFc, 0, sizeof(float2) * LL * n_tiles, c->stream));
+  CK(cudaMemsetAsync(c->objCrop, 0, sizeof(float2) * LL * n_tiles, c->stream));
+  CK(cudaMemsetAsync(c->pupil, 0, sizeof(float2) * NN * n_tiles, c->stream));
+  CK(cudaMemsetAsync(c->scratch, 0, sizeof(float2) * c->scratch_elems, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   int rc;
-  if ((rc = upload_twiddles(c->twN, Np)) != FPMB200_OK) return rc;
-  if ((rc = upload_twiddles(c->twL, Nlarge)) != FPMB200_OK) return rc;
+  if ((rc = upload_twiddles(c, c->twN, Np)) != FPMB200_OK) return rc;
+  if ((rc = upload_twiddles(c, c->twL, Nlarge)) != FPMB200_OK) return rc;
   snprintf(c->variant, sizeof c->variant, "allocated (support not uploaded yet)");
   return FPMB200_OK;
 }
@@ -166,7 +177,7 @@ extern "C" int fpmb200_upload_leds(fpmb200_ctx* c, const int16_t* cx, const int1
     h[k] = make_short2(cx[k], cy[k]);
   }
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpy(c->crop, h.data(), sizeof(short2) * n_leds, cudaMemcpyHostToDevice));
+  CK(copy_sync(c, c->crop, h.data(), sizeof(short2) * n_leds, cudaMemcpyHostToDevice));
   c->have_leds = true;
   return FPMB200_OK;
 }
@@ -197,7 +208,7 @@ extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
   if (yhi < ylo) return fail(FPMB200_ERR_ARG, "pupil support is empty");
   c->ylo = ylo; c->yhi = yhi; c->xlo = xlo; c->xhi = xhi;
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpy(c->support, mask, sizeof(float) * N * N, cudaMemcpyHostToDevice));
+  CK(copy_sync(c, c->support, mask, sizeof(float) * N * N, cudaMemcpyHostToDevice));
   c->have_support = true;
   // ---- choose the kernel variant for this (N, L, bbox) ----
   const size_t cap = (size_t)c->max_smem_optin;
@@ -355,12 +366,12 @@ extern "C" int fpmb200_upload_state(fpmb200_ctx* c, int tile, const float* objF,
   const size_t LL = (size_t)c->L * c->L, NN = (size_t)c->N * c->N;
   CK(cudaDeviceSynchronize());
   if (objF) {
-    CK(cudaMemcpy(c->scratch, objF, sizeof(float2) * LL, cudaMemcpyHostToDevice));
+    CK(copy_sync(c, c->scratch, objF, sizeof(float2) * LL, cudaMemcpyHostToDevice));
     shift_copy_kernel<<<dim3(64, 1), 256, 0, c->stream>>>(c->objFc + LL * tile, c->scratch, c->L, 0, 0);
     c->launches++;
     CK(cudaStreamSynchronize(c->stream));
   }
-  if (pupil) CK(cudaMemcpy(c->pupil + NN * tile, pupil, sizeof(float2) * NN, cudaMemcpyHostToDevice));
+  if (pupil) CK(copy_sync(c, c->pupil + NN * tile, pupil, sizeof(float2) * NN, cudaMemcpyHostToDevice));
   return FPMB200_OK;
 }
 
@@ -374,10 +385,10 @@ extern "C" int fpmb200_download(fpmb200_ctx* c, int tile, float* objF, float* ob
     shift_copy_kernel<<<dim3(64, 1), 256, 0, c->stream>>>(c->scratch, c->objFc + LL * tile, c->L, 0, 0);
     c->launches++;
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(objF, c->scratch, sizeof(float2) * LL, cudaMemcpyDeviceToHost));
+    CK(copy_sync(c, objF, c->scratch, sizeof(float2) * LL, cudaMemcpyDeviceToHost));
   }
-  if (objCrop) CK(cudaMemcpy(objCrop, c->objCrop + LL * tile, sizeof(float2) * LL, cudaMemcpyDeviceToHost));
-  if (pupil) CK(cudaMemcpy(pupil, c->pupil + NN * tile, sizeof(float2) * NN, cudaMemcpyDeviceToHost));
+  if (objCrop) CK(copy_sync(c, objCrop, c->objCrop + LL * tile, sizeof(float2) * LL, cudaMemcpyDeviceToHost));
+  if (pupil) CK(copy_sync(c, pupil, c->pupil + NN * tile, sizeof(float2) * NN, cudaMemcpyDeviceToHost));
   return FPMB200_OK;
 }
 
@@ -389,6 +400,23 @@ extern "C" int fpmb200_download_objcrop(fpmb200_ctx* c, int first, int n, float*
   const size_t LL = (size_t)c->L * c->L;
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   CK(cudaMemcpyAsync(objCrop, c->objCrop + LL * first, sizeof(float2) * LL * n, cudaMemcpyDeviceToHost, st));
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_device_buffer(fpmb200_ctx* c, int which, int tile, void** ptr, unsigned long long* bytes) {
+  int rc = check_range(c, tile, 1);
+  if (rc) return rc;
+  if (!ptr) return fail(FPMB200_ERR_ARG, "ptr is NULL");
+  const size_t LL = (size_t)c->L * c->L, NN = (size_t)c->N * c->N;
+  size_t b = 0;
+  switch (which) {
+    case 0: b = sizeof(float2) * LL; *ptr = c->objFc + LL * tile; break;
+    case 1: b = sizeof(float2) * LL; *ptr = c->objCrop + LL * tile; break;
+    case 2: b = sizeof(float2) * NN; *ptr = c->pupil + NN * tile; break;
+    case 3: b = sizeof(uint16_t) * NN * c->n_leds; *ptr = c->stack + NN * c->n_leds * tile; break;
+    default: return fail(FPMB200_ERR_ARG, "which=%d not in 0..3", which);
+  }
+  if (bytes) *bytes = b;
   return FPMB200_OK;
 }
 

@@ -50,6 +50,7 @@ def load():
         "fpmb200_upload_state": (i, [vp, i, vp, vp]),
         "fpmb200_download": (i, [vp, i, vp, vp, vp]),
         "fpmb200_download_objcrop": (i, [vp, i, i, vp, vp]),
+        "fpmb200_device_buffer": (i, [vp, i, i, C.POINTER(vp), C.POINTER(C.c_ulonglong)]),
         "fpmb200_sync": (i, [vp]),
         "fpmb200_kernel_launches": (C.c_longlong, [vp]),
         "fpmb200_variant": (C.c_char_p, [vp]),
@@ -65,7 +66,7 @@ EXPORTS = ["fpmb200_last_error", "fpmb200_abi_version", "fpmb200_create", "fpmb2
            "fpmb200_tiles_alloc", "fpmb200_set_params", "fpmb200_upload_leds",
            "fpmb200_upload_pupil_support", "fpmb200_upload_stack", "fpmb200_init_tiles", "fpmb200_run",
            "fpmb200_step", "fpmb200_finalize", "fpmb200_upload_state", "fpmb200_download",
-           "fpmb200_download_objcrop", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
+           "fpmb200_download_objcrop", "fpmb200_device_buffer", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
 
 
 class FpmError(RuntimeError):
@@ -157,6 +158,21 @@ class Context:
 
     def download_objcrop_ptr(self, tile_first, n, host_ptr, stream=None):
         self._ck(self.L.fpmb200_download_objcrop(self._h, tile_first, n, C.c_void_p(host_ptr), stream))
+
+    def device_buffer(self, which, tile=0):
+        """(device pointer, bytes per tile) of objFc(0) / objCrop(1) / pupil(2) / stack(3)."""
+        p, b = C.c_void_p(), C.c_ulonglong()
+        self._ck(self.L.fpmb200_device_buffer(self._h, which, tile, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def objcrop_tensor(self, tile_first, n):
+        """torch view (no copy) of objCrop of n tiles: float32 [n, Nlarge*Nlarge*2] on this device."""
+        import torch
+        ptr, b = self.device_buffer(1, tile_first)
+
+        class _V:
+            __cuda_array_interface__ = {"shape": (n, b // 4), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_V(), device="cuda")
 
     def sync(self):
         self._ck(self.L.fpmb200_sync(self._h))

@@ -1,0 +1,51 @@
+"""Synthetic intensity stacks -- input-data plumbing for tests and bench.py.
+
+The reference ships no images (`datasetRoot` are absolute /Users/... paths), so stacks are produced
+with the reference's own forward model: crop of the centred spectrum of a seeded ground-truth object
+at (cropYStart, cropXStart) -> multiply by the disc pupil -> inverse FFT -> |.|^2, scaled so the
+global maximum is 60000 and rounded to uint16.  numpy only; nothing here is on the timed path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _sh(a):
+    return np.roll(a, (a.shape[0] // 2, a.shape[1] // 2), axis=(0, 1))
+
+
+def disc_support(N: int, r: int) -> np.ndarray:
+    y, x = np.mgrid[0:N, 0:N]
+    return _sh(((x - N // 2) ** 2 + (y - N // 2) ** 2 <= r * r).astype(np.float64))
+
+
+def synth_object(L: int, seed: int, sigma: float = 0.1) -> np.ndarray:
+    """amp = 0.3 + 0.7*G1 (G1 in [0,1]), phase = G2/max|G2| rad; G = Gaussian-low-passed white noise
+    (sigma cycles/pixel: 0.1 puts signal under the dark-field LEDs too)."""
+    rng = np.random.default_rng(seed)
+    fy = np.fft.fftfreq(L)[:, None]
+    fx = np.fft.fftfreq(L)[None, :]
+    lp = np.exp(-(fx * fx + fy * fy) / (2 * sigma ** 2))
+
+    def smooth():
+        w = rng.standard_normal((L, L))
+        return np.real(np.fft.ifft2(np.fft.fft2(w) * lp))
+
+    g1 = smooth()
+    g1 = (g1 - g1.min()) / (g1.max() - g1.min())
+    g2 = smooth()
+    g2 = g2 / np.abs(g2).max()
+    return (0.3 + 0.7 * g1) * np.exp(1j * g2)
+
+
+def synth_stack(N: int, L: int, naRadius: int, cropX, cropY, seed: int) -> np.ndarray:
+    """uint16 [n_leds][N][N], slot k imaged through the window at (cropY[k], cropX[k])."""
+    obj = synth_object(L, seed)
+    Fc = np.fft.fftshift(np.fft.fft2(obj))
+    S = disc_support(N, naRadius)
+    out = np.empty((len(cropX), N, N), dtype=np.float64)
+    for k, (xs, ys) in enumerate(zip(cropX, cropY)):
+        xs, ys = int(xs), int(ys)
+        out[k] = np.abs(np.fft.ifft2(_sh(Fc[ys:ys + N, xs:xs + N]) * S)) ** 2
+    out *= 60000.0 / out.max()
+    return np.rint(out).astype(np.uint16)

@@ -89,6 +89,11 @@ int fpmb200_download(fpmb200_ctx* ctx, int tile, float* objF, float* objCrop, fl
 /* Asynchronous gather of objCrop of tiles [tile_first,tile_first+n) into pinned host memory. */
 int fpmb200_download_objcrop(fpmb200_ctx* ctx, int tile_first, int n, float* objCrop, void* stream);
 
+/* Device pointer of tile `tile`'s buffer for zero-copy hand-off (e.g. the final NCCL gather of a
+ * multi-GPU run): which = 0 centred spectrum [Nlarge][Nlarge][2] float, 1 objCrop, 2 pupil,
+ * 3 intensity stack (uint16).  Consecutive tiles are contiguous. */
+int fpmb200_device_buffer(fpmb200_ctx* ctx, int which, int tile, void** ptr, unsigned long long* bytes_per_tile);
+
 int fpmb200_sync(fpmb200_ctx* ctx);
 
 /* Introspection: kernels launched by this context so far, and the name/shape of the update

@@ -278,7 +278,7 @@ def libstdcxx_sort_indexes(v) -> list:
 
 
 # --------------------------------------------------------------------------- #
-# pupil support, synthetic stacks
+# pupil support (synthetic stacks live in fpm-opencv_b200/synth.py: input plumbing, not oracle)
 # --------------------------------------------------------------------------- #
 def sh(a: np.ndarray) -> np.ndarray:
     """cvComplex fftShift on even sizes: circular shift by half (R2)."""
@@ -292,39 +292,6 @@ def pupil_support(N: int, r: int) -> np.ndarray:
     y, x = np.mgrid[0:N, 0:N]
     disc = ((x - N // 2) ** 2 + (y - N // 2) ** 2 <= r * r).astype(np.float64)
     return sh(disc)
-
-
-def synth_object(L: int, seed: int) -> np.ndarray:
-    """Ground-truth object of SURVEY 8d: amp = 0.3+0.7*G1, phase = G2/max|G2| rad."""
-    rng = np.random.default_rng(seed)
-    fy = np.fft.fftfreq(L)[:, None]
-    fx = np.fft.fftfreq(L)[None, :]
-    lp = np.exp(-(fx * fx + fy * fy) / (2 * 0.1 ** 2))   # sigma 0.1 cyc/px: dark-field LEDs carry signal
-
-    def smooth():
-        w = rng.standard_normal((L, L))
-        return np.real(np.fft.ifft2(np.fft.fft2(w) * lp))
-
-    g1 = smooth()
-    g1 = (g1 - g1.min()) / (g1.max() - g1.min())
-    g2 = smooth()
-    g2 = g2 / np.abs(g2).max()
-    return (0.3 + 0.7 * g1) * np.exp(1j * g2)
-
-
-def synth_stack(N: int, L: int, naRadius: int, cropX, cropY, seed: int) -> np.ndarray:
-    """uint16 stack [n_leds][N][N] from the reference's own forward model:
-    crop of the centred spectrum at (cropY,cropX) -> * disc pupil -> IFFT -> |.|^2,
-    scaled to max 60000 and rounded."""
-    obj = synth_object(L, seed)
-    Fc = np.fft.fftshift(np.fft.fft2(obj))
-    S = pupil_support(N, naRadius)
-    out = np.empty((len(cropX), N, N), dtype=np.float64)
-    for k, (xs, ys) in enumerate(zip(cropX, cropY)):
-        O = sh(Fc[ys : ys + N, xs : xs + N])
-        out[k] = np.abs(np.fft.ifft2(O * S)) ** 2
-    out *= 60000.0 / out.max()
-    return np.rint(out).astype(np.uint16)
 
 
 # --------------------------------------------------------------------------- #

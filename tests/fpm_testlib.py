@@ -6,6 +6,7 @@ import os
 import numpy as np
 
 import fpm_oracle as orc
+import synth
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -39,7 +40,7 @@ class Case:
         self.cy = np.array([byn[n]["cropY"] for n in order], np.int16)
         c = self.cfg
         self.N, self.L, self.r = c.Np, c.Nlarge, c.naRadius
-        self.stack = orc.synth_stack(c.Np, c.Nlarge, c.naRadius, self.cx, self.cy, seed)
+        self.stack = synth.synth_stack(c.Np, c.Nlarge, c.naRadius, self.cx, self.cy, seed)
         self.support = orc.pupil_support(c.Np, c.naRadius)
 
     def oracle_run(self, iters, kappa=1, trace=None):

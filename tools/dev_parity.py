@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.joi
 import numpy as np
 import fpm_oracle as o
 import fpmb200
+import synth
 
 def setup(name, seed):
     g = json.load(open(os.path.join(ROOT, "tests/golden/geometry_%s.json" % name)))
@@ -12,7 +13,7 @@ def setup(name, seed):
     cfg = o.config_from_json(j)
     byn = {l["n"]: l for l in g["leds"]}
     cx = [byn[n]["cropX"] for n in g["order"]]; cy = [byn[n]["cropY"] for n in g["order"]]
-    st = o.synth_stack(cfg.Np, cfg.Nlarge, cfg.naRadius, cx, cy, seed)
+    st = synth.synth_stack(cfg.Np, cfg.Nlarge, cfg.naRadius, cx, cy, seed)
     return cfg, cx, cy, st
 
 def main():
