@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.sm_max, self._stop = index, [], set(), None, threading.Event()
+        self.index, self.samples, self.reasons, self.sm_max, self._halt = index, [], set(), None, threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
                  "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.02)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
