@@ -143,8 +143,12 @@ def run_b200(args):
     ctx.upload_stack_ptr(0, tiles, host_in.data_ptr(), None)
     ctx.sync()
 
-    main = torch.cuda.current_stream()
+    # a real (non-NULL) stream: the C ABI treats stream==NULL as "the context's own stream", and
+    # torch.cuda.Event only sees work enqueued on the stream it is recorded on
+    main = torch.cuda.Stream()
+    torch.cuda.set_stream(main)
     sp = main.cuda_stream
+    assert sp != 0
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def barrier():
