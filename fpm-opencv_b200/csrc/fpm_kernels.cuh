@@ -27,6 +27,12 @@
 #include <stdint.h>
 #include "fft_regs.cuh"
 
+#ifdef FPM_STAGE_TIMING
+#define FPM_TICK(k) do { if (tid == 0 && blockIdx.x == 0) { long long t_ = clock64(); p.stage_clk[k] += t_ - tprev_; tprev_ = t_; } } while (0)
+#else
+#define FPM_TICK(k) do {} while (0)
+#endif
+
 namespace fpm {
 
 struct UpdateParams {
@@ -43,6 +49,7 @@ struct UpdateParams {
   float delta1, delta2, eps, kappa;
   int ylo, yhi, xlo, xhi;   // support bbox (wrapped)
   int bs;                   // log2 of the block-max grid cell edge (3,4,5)
+  long long* stage_clk;     // [16] per-stage cycle totals of CTA 0 (only with -DFPM_STAGE_TIMING)
 };
 
 template <int N> struct Radix {
@@ -134,6 +141,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   const float kd1 = p.kappa * p.delta1, kd2 = p.kappa * p.delta2;
   const float epsr = p.eps, epsi = p.kappa * p.eps;
 
+#ifdef FPM_STAGE_TIMING
+  long long tprev_ = clock64();
+#endif
   for (int u = 0; u < p.n_updates; ++u) {
     const int slot = (p.slot_begin + u) % p.n_leds;
     const short2 cr = p.crop[slot];
@@ -170,6 +180,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       }
     }
     __syncthreads();
+    FPM_TICK(1);
     // ================= S2: cols stage B (inverse) =================
     for (int g = tid; g < R1 * NC; g += NT) {
       const int k1 = g / NC, jc = g - k1 * NC;
@@ -182,6 +193,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       for (int a = 0; a < R2; ++a) fld[(R2 * k1 + a) * PITCH + js] = v[a];
     }
     __syncthreads();
+    FPM_TICK(2);
     // ================= S3: rows stage A (inverse) =================
     for (int g = tid; g < N * R2; g += NT) {
       const int row = g / R2, j0 = g % R2;
@@ -194,6 +206,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       for (int k1 = 0; k1 < R1; ++k1) rp[swz(j0 + R2 * k1)] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
     }
     __syncthreads();
+    FPM_TICK(3);
     // ===== S4: rows stage B (inverse) + amplitude replacement + rows stage B' (forward) =====
     for (int g = tid; g < N * R1; g += NT) {
       const int row = g / R1, k1 = g % R1;
@@ -220,6 +233,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       for (int q = 0; q < R2; ++q) rp[swz(R2 * k1 + q)] = twmul<false>(v[q], twB[q * R1 + k1]);
     }
     __syncthreads();
+    FPM_TICK(4);
     // ================= S5: rows stage A' (forward) =================
     for (int g = tid; g < N * R2; g += NT) {
       const int row = g / R2, q = g % R2;
@@ -232,6 +246,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       for (int r = 0; r < R1; ++r) rp[swz(R2 * r + q)] = v[r];
     }
     __syncthreads();
+    FPM_TICK(5);
     // ================= S6: cols stage B' (forward) =================
     for (int g = tid; g < R1 * NC; g += NT) {
       const int k1 = g / NC, jc = g - k1 * NC;
@@ -244,6 +259,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       for (int q = 0; q < R2; ++q) fld[(R2 * k1 + q) * PITCH + js] = twmul<false>(v[q], twB[q * R1 + k1]);
     }
     __syncthreads();
+    FPM_TICK(6);
     // ================= S7: cols stage A' (forward) -> Phi' in natural order =================
     for (int g = tid; g < R2 * NC; g += NT) {
       const int q = g / NC, jc = g - q * NC;
@@ -256,6 +272,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       for (int r = 0; r < R1; ++r) fld[(R2 * r + q) * PITCH + js] = v[r];
     }
     __syncthreads();
+    FPM_TICK(7);
     // ================= S8: object update + block maxima (fpmMain.cpp:406-447) =================
     float pm2 = red[32];
 #pragma unroll
@@ -310,6 +327,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       }
     }
     __syncthreads();
+    FPM_TICK(8);
     // ---- max |objF| over the whole updated spectrum (fpmMain.cpp:460,467) ----
     {
       float m = 0.f;
@@ -318,6 +336,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       if (lane == 0) red[warp] = m;
     }
     __syncthreads();
+    FPM_TICK(9);
     float om2 = red[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) om2 = fmaxf(om2, red[w]);
@@ -337,6 +356,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     pnew = warp_max(pnew);
     if (lane == 0) red[32 + warp] = pnew;   // last read of red[32..] was before two barriers (S8)
     __syncthreads();
+    FPM_TICK(10);
   }
 
   if constexpr (P_SMEM) {

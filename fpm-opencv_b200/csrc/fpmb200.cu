@@ -57,6 +57,7 @@ struct fpmb200_ctx {
   size_t smem_bytes = 0;
   int max_smem_optin = 0, sm_count = 0;
   long long launches = 0;
+  long long* stage_clk = nullptr;
   char variant[160] = "unallocated";
 };
 
@@ -322,6 +323,10 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
   p.slot_begin = slot_begin; p.n_updates = n_updates;
   p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
   p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi; p.bs = c->bs;
+#ifdef FPM_STAGE_TIMING
+  if (!c->stage_clk) { CK(cudaMalloc(&c->stage_clk, 16 * sizeof(long long))); CK(cudaMemset(c->stage_clk, 0, 16 * sizeof(long long))); }
+  p.stage_clk = c->stage_clk;
+#endif
   CK(cudaSetDevice(c->device));
   switch (c->N) {
     case 64: return launch_update<64, 256, 3>(c, p, n, st);
@@ -427,5 +432,14 @@ extern "C" int fpmb200_sync(fpmb200_ctx* c) {
   return FPMB200_OK;
 }
 
+#ifdef FPM_STAGE_TIMING
+extern "C" int fpmb200_stage_clocks(fpmb200_ctx* c, long long* out16) {
+  if (!c || !c->stage_clk) return -1;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out16, c->stage_clk, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(c->stage_clk, 0, 16 * sizeof(long long));
+  return 0;
+}
+#endif
 extern "C" long long fpmb200_kernel_launches(const fpmb200_ctx* c) { return c ? c->launches : 0; }
 extern "C" const char* fpmb200_variant(const fpmb200_ctx* c) { return c ? c->variant : ""; }

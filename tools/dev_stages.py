@@ -1,0 +1,27 @@
+"""Developer script: per-stage cycle breakdown of the update kernel (timing build)."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fpm-opencv_b200"), os.path.join(ROOT, "tests")]
+import numpy as np
+import fpmb200
+fpmb200.lib_path = lambda: os.path.join(fpmb200.LIB_DIR, "libfpmb200_timing.so")
+import fpm_testlib as T
+names = sys.argv[1:] or ["cfg2_fLEDc_np128"]
+for name in names:
+    c = T.Case(name, 1)
+    for n_tiles in (1, 148):
+        ctx = c.make_ctx(n_tiles=n_tiles)
+        ctx.run(1); ctx.sync()
+        buf = (C.c_longlong * 16)()
+        ctx.L.fpmb200_stage_clocks.argtypes = [C.c_void_p, C.c_void_p]
+        ctx.L.fpmb200_stage_clocks(ctx._h, buf)
+        ctx.run(2); ctx.sync()
+        ctx.L.fpmb200_stage_clocks(ctx._h, buf)
+        n_upd = 2 * len(c.cx)
+        v = np.array(list(buf), dtype=np.float64) / n_upd
+        labels = ["-", "S1 colA+load", "S2 colB", "S3 rowA", "S4 rowB+amp+rowB'", "S5 rowA'", "S6 colB'", "S7 colA'", "S8 objupd+cells", "G1 reduce", "S9 pupil"]
+        print(name, "tiles", n_tiles, ctx.variant)
+        for k in range(1, 11):
+            print("   %-20s %8.0f cyc  %5.1f%%" % (labels[k], v[k], 100 * v[k] / v[1:11].sum()))
+        print("   total %.0f cycles/update" % v[1:11].sum())
+        ctx.close()
