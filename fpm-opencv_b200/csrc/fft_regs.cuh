@@ -4,34 +4,35 @@
 // arrays live in registers.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace fpm {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 // a * conj(b)
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+__host__ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
 // multiply by -i (forward quarter turn) or +i (inverse)
-template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) {
+template <bool INV> __host__ __device__ __forceinline__ float2 rot90(float2 a) {
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
 // multiply by twiddle w (forward table) or its conjugate
-template <bool INV> __device__ __forceinline__ float2 twmul(float2 a, float2 w) {
+template <bool INV> __host__ __device__ __forceinline__ float2 twmul(float2 a, float2 w) {
   return INV ? cmulc(a, w) : cmul(a, w);
 }
 
-template <bool INV> __device__ __forceinline__ void fft2(float2& a, float2& b) {
+template <bool INV> __host__ __device__ __forceinline__ void fft2(float2& a, float2& b) {
   float2 t = a;
   a = cadd(t, b);
   b = csub(t, b);
 }
 
-template <bool INV> __device__ __forceinline__ void fft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+template <bool INV> __host__ __device__ __forceinline__ void fft4(float2& x0, float2& x1, float2& x2, float2& x3) {
   float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = rot90<INV>(csub(x1, x3));
   x0 = cadd(t0, t2);
   x2 = csub(t0, t2);
@@ -39,7 +40,7 @@ template <bool INV> __device__ __forceinline__ void fft4(float2& x0, float2& x1,
   x3 = csub(t1, t3);
 }
 
-template <bool INV> __device__ __forceinline__ void fft3(float2& x0, float2& x1, float2& x2) {
+template <bool INV> __host__ __device__ __forceinline__ void fft3(float2& x0, float2& x1, float2& x2) {
   const float s = INV ? 0.86602540378443864676f : -0.86602540378443864676f;   // Im(W3)
   float2 t1 = cadd(x1, x2);
   float2 t2 = make_float2(fmaf(-0.5f, t1.x, x0.x), fmaf(-0.5f, t1.y, x0.y));
@@ -50,7 +51,7 @@ template <bool INV> __device__ __forceinline__ void fft3(float2& x0, float2& x1,
   x2 = csub(t2, t3);
 }
 
-template <bool INV> __device__ __forceinline__ void fft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
+template <bool INV> __host__ __device__ __forceinline__ void fft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
   const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;    // cos(2pi/5), cos(4pi/5)
   const float s1 = INV ? 0.95105651629515357212f : -0.95105651629515357212f;  // +-sin(2pi/5)
   const float s2 = INV ? 0.58778525229247312917f : -0.58778525229247312917f;  // +-sin(4pi/5)
@@ -69,16 +70,16 @@ template <bool INV> __device__ __forceinline__ void fft5(float2& x0, float2& x1,
 }
 
 // (1 -+ i)/sqrt2 and (-1 -+ i)/sqrt2 multiplications
-template <bool INV> __device__ __forceinline__ float2 mulW8_1(float2 a) {
+template <bool INV> __host__ __device__ __forceinline__ float2 mulW8_1(float2 a) {
   const float h = 0.70710678118654752440f;
   return INV ? make_float2(h * (a.x - a.y), h * (a.x + a.y)) : make_float2(h * (a.x + a.y), h * (a.y - a.x));
 }
-template <bool INV> __device__ __forceinline__ float2 mulW8_3(float2 a) {
+template <bool INV> __host__ __device__ __forceinline__ float2 mulW8_3(float2 a) {
   const float h = 0.70710678118654752440f;
   return INV ? make_float2(-h * (a.x + a.y), h * (a.x - a.y)) : make_float2(h * (a.y - a.x), -h * (a.x + a.y));
 }
 
-template <bool INV> __device__ __forceinline__ void fft8(float2 (&v)[8]) {
+template <bool INV> __host__ __device__ __forceinline__ void fft8(float2 (&v)[8]) {
   // DIT: even / odd quarter transforms, then W8^k combine
   fft4<INV>(v[0], v[2], v[4], v[6]);
   fft4<INV>(v[1], v[3], v[5], v[7]);
@@ -92,7 +93,7 @@ template <bool INV> __device__ __forceinline__ void fft8(float2 (&v)[8]) {
 }
 
 // multiply by W16^n (forward) or its conjugate, n compile-time in [0,9]
-template <bool INV, int n> __device__ __forceinline__ float2 mulW16(float2 a) {
+template <bool INV, int n> __host__ __device__ __forceinline__ float2 mulW16(float2 a) {
   if constexpr (n == 0) return a;
   else if constexpr (n == 2) return mulW8_1<INV>(a);
   else if constexpr (n == 4) return rot90<INV>(a);
@@ -104,7 +105,7 @@ template <bool INV, int n> __device__ __forceinline__ float2 mulW16(float2 a) {
   }
 }
 
-template <bool INV> __device__ __forceinline__ void fft16(float2 (&v)[16]) {
+template <bool INV> __host__ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
   // radix-4 DIT: four stride-4 sub-transforms A_j (j = 0..3) ...
   fft4<INV>(v[0], v[4], v[8], v[12]);
   fft4<INV>(v[1], v[5], v[9], v[13]);
@@ -126,8 +127,76 @@ template <bool INV> __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 #undef FPM_SWAP
 }
 
-template <int R, bool INV> __device__ __forceinline__ void fftR(float2 (&v)[R]) {
-  if constexpr (R == 16) fft16<INV>(v);
+// ---- compile-time loop and 32nd roots of unity -------------------------------------------
+template <int B, int E, class F> __host__ __device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+__host__ __device__ constexpr float cos32(int n) {
+  constexpr float t[32] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f,
+                           0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f, 0.f, -0.19509032201612819f,
+                           -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254535f,
+                           -0.92387953251128674f, -0.98078528040323043f, -1.f, -0.98078528040323043f, -0.92387953251128685f,
+                           -0.83146961230254546f, -0.70710678118654768f, -0.55557023301960218f, -0.38268343236509034f,
+                           -0.19509032201612866f, 0.f, 0.1950903220161283f, 0.38268343236509f, 0.55557023301960184f,
+                           0.70710678118654735f, 0.83146961230254524f, 0.92387953251128652f, 0.98078528040323032f};
+  return t[n & 31];
+}
+__host__ __device__ constexpr float sin32(int n) { return cos32(n + 24); }   // sin(x) = cos(x - pi/2)
+
+// a * exp(-2*pi*i*n/32)  (INV: exp(+...)), n compile-time
+template <bool INV, int n> __host__ __device__ __forceinline__ float2 mulW32(float2 a) {
+  constexpr int m = n & 31;
+  if constexpr (m == 0) return a;
+  else if constexpr (m == 8) return rot90<INV>(a);
+  else if constexpr (m == 16) return make_float2(-a.x, -a.y);
+  else if constexpr (m == 24) return rot90<!INV>(a);
+  else if constexpr (m == 4) return mulW8_1<INV>(a);
+  else if constexpr (m == 12) return mulW8_3<INV>(a);
+  else {
+    constexpr float c = cos32(m), s = -sin32(m);      // forward twiddle c + i*s
+    return twmul<INV>(a, make_float2(c, s));
+  }
+}
+
+template <bool INV> __host__ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
+  // radix-4 x radix-8 DIT: four stride-4 sub-transforms A_j (8 points each) ...
+  static_for<0, 4>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    float2 t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = v[j + 4 * k];
+    fft8<INV>(t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[j + 4 * k] = t[k];   // A_j[k] in slot j + 4k
+  });
+  // ... twiddled by W32^(j*k) ...
+  static_for<1, 4>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    static_for<1, 8>([&](auto K) {
+      constexpr int k = decltype(K)::value;
+      v[j + 4 * k] = mulW32<INV, j * k>(v[j + 4 * k]);
+    });
+  });
+  // ... then eight 4-point transforms over j give X[k + 8q] in slot 4k + q
+#pragma unroll
+  for (int k = 0; k < 8; ++k) fft4<INV>(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  // slot 4k+q -> natural index k + 8q
+  float2 o[32];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[k + 8 * q] = v[4 * k + q];
+#pragma unroll
+  for (int n = 0; n < 32; ++n) v[n] = o[n];
+}
+
+template <int R, bool INV> __host__ __device__ __forceinline__ void fftR(float2 (&v)[R]) {
+  if constexpr (R == 32) fft32<INV>(v);
+  else if constexpr (R == 16) fft16<INV>(v);
   else if constexpr (R == 8) fft8<INV>(v);
   else if constexpr (R == 4) fft4<INV>(v[0], v[1], v[2], v[3]);
   else if constexpr (R == 2) fft2<INV>(v[0], v[1]);

@@ -1,0 +1,523 @@
+// fpm_update.cuh -- the fused sub-aperture update kernel (sm_100a).
+//
+// One CTA per tile, persistent over the whole (iteration x LED) sequence of that tile: the low-res
+// exit-wave field never leaves shared memory between "crop * pupil" and the object / pupil update.
+// Restates one body of the loop nest fpmMain.cpp:345-476 per "update" (SURVEY.md appendix A).
+//
+// Index conventions
+//   window (i,j)      DC-at-corner, the reference's Objfcrop (fpmMain.cpp:361)
+//   wrapped (iw,jw)   iw = i < N/2 ? i : i-N
+//   absolute (r,c)    centred spectrum objFc: r = ys + N/2 + iw, c = xs + N/2 + jw  (the two fftShifts of
+//                     fpmMain.cpp:358,361 folded into addressing)
+//   support bbox      wrapped ranges [ylo,yhi] x [xlo,xhi] containing every non-zero pupilSupport pixel.
+//                     P == 0 outside it for ever (P starts as the support, every increment is masked:
+//                     fpmMain.cpp:313,472), so O*P, dO and dP vanish there and everything that touches
+//                     P is restricted to the bbox with bit-identical results.
+//
+// N x N transform, separable, N = R1*R2 per dimension (64 = 8*8, 128 = 16*8, 256 = 16*16): four
+// in-register radix stages per transform, the field exchanged through shared memory in between.
+//   IFFT (DIF, natural in -> digit-scrambled out):  S1 cols-A, S2 cols-B, S3 rows-A, S4 rows-B
+//   FFT  (DIT, scrambled in -> natural out):        S4 rows-B', S5 rows-A', S6 cols-B', S7 cols-A'
+// S4 runs the last inverse stage, the amplitude replacement (fpmMain.cpp:378-393) and the first forward
+// stage on the same registers; scrambled position p = R2*k1 + k2 holds index k1 + R1*k2, so no reorder
+// pass exists.  Column stages only visit bbox columns; S3 reads bbox columns only (the rest is zero).
+//   C2  object update on the bbox (fpmMain.cpp:406-447); the window O was prefetched into shared memory
+//       during the previous update; Q = pupil-update numerator replaces it in place
+//   D   exact max|objF| (fpmMain.cpp:460,467) from a grid of (2^cs rows x 32 columns) cell maxima: one
+//       warp per touched cell-row refreshes its cells and the row maximum; untouched rows are reused
+//   E   P += Q / max|objF| (fpmMain.cpp:459-475), max|P| and the window of the next LED
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fft_regs.cuh"
+
+#ifdef FPM_STAGE_TIMING
+#define FPM_TICK(k) do { long long t_ = clock64(); tacc_[k] += t_ - tprev_; tprev_ = t_; } while (0)   /* registers only */
+#else
+#define FPM_TICK(k) do {} while (0)
+#endif
+
+namespace fpm {
+
+struct UpdateParams {
+  float2* objFc;            // [n_tiles][L][L]   centred spectrum
+  float2* pupil;            // [n_tiles][N][N]   DC-at-corner
+  const uint16_t* stack;    // [n_tiles][n_leds][N*N] in the permuted device layout (stack_offset below)
+  const float* support;     // [N][N]
+  const short2* crop;       // [n_leds] (x = cropXStart, y = cropYStart)
+  const float2* tw;         // [N] exp(-2*pi*i*n/N)
+  float2* field_gmem;       // [n_tiles][N][N+1] scratch when the field does not fit shared memory
+  float2* qbuf;             // [n_tiles][N][N] pupil-increment scratch when it does not fit shared memory
+  int L, n_leds;
+  int tile0;                // first tile of this launch
+  int slot_begin, n_updates;
+  float delta1, delta2, eps, kappa;
+  int ylo, yhi, xlo, xhi;   // support bbox (wrapped)
+  int cs;                   // log2 rows per max-cell (cells are (1<<cs) rows x 32 columns)
+  long long* stage_clk;     // [16] per-stage cycle totals of CTA 0 (only with -DFPM_STAGE_TIMING)
+};
+
+template <int N> struct Shape {
+  static constexpr int R1 = (N == 64) ? 8 : 16;
+  static constexpr int R2 = N / R1;
+  static constexpr int PITCH = N + 8;       // float2 per field row; == 8 (mod 16): row passes conflict-free
+  static constexpr int CH = R2 / 8;         // uint4 intensity chunks per S4 work item
+};
+
+// in-row XOR swizzle (bijective on aligned 128-blocks): lets the stride-1 radix stage (each lane owns R2
+// consecutive complex) hit 16 distinct 8-byte bank pairs per half-warp
+__host__ __device__ __forceinline__ int swz(int j) { return j ^ ((j >> 3) & 15); }
+
+// Device layout of one N x N intensity image: the R2 pixels an S4 work item needs (scrambled row
+// position p <-> spatial row y = p/R2 + R1*(p%R2); columns x = k1 + R1*k2) are contiguous.
+// Returns the uint16 offset of pixel (y, x).
+template <int N> __host__ __device__ __forceinline__ int stack_offset(int y, int x) {
+  using S = Shape<N>;
+  const int pos = S::R2 * (y % S::R1) + y / S::R1;
+  return (pos * S::R1 + (x % S::R1)) * S::R2 + x / S::R1;
+}
+
+// maximum of non-negative floats over a warp: one REDUX on the bit patterns (order-preserving for v >= 0)
+#ifndef FPM_EXP
+#define FPM_EXP 0
+#endif
+__device__ __forceinline__ float warp_max(float v) {
+#if FPM_EXP & 2
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+#else
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+#endif
+}
+__device__ __forceinline__ float half_warp_max(float v, int lane) {
+#if FPM_EXP & 2
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+#else
+  return __uint_as_float(__reduce_max_sync((lane & 16) ? 0xffff0000u : 0x0000ffffu, __float_as_uint(v)));
+#endif
+}
+__device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+template <int N, int NT, int MINB, bool FIELD_SMEM, bool P_SMEM, bool Q_SMEM>
+__global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams p) {
+  using S = Shape<N>;
+  constexpr int R1 = S::R1, R2 = S::R2, PITCH = S::PITCH, CH = S::CH;
+  constexpr int H = N / 2, NW = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = p.tile0 + blockIdx.x;
+  const int L = p.L;
+  const int NR = p.yhi - p.ylo + 1, NC = p.xhi - p.xlo + 1;
+  const int gc = L >> 4, gr = L >> p.cs;                 // max-cells are (1<<cs) rows x 16 columns
+  const int tmr = (NR >> p.cs) + 2, tmc = (NC >> 4) + 2;   // cells a bbox rectangle can touch
+
+  // ---- shared memory carve-up ----
+  unsigned char* sp = smem_raw;
+  float2* fld;
+  if constexpr (FIELD_SMEM) { fld = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * N * PITCH; }
+  else fld = p.field_gmem + (size_t)tile * N * PITCH;
+  float2* twA = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * N;   // [b*R2 + a] = W^(a*b)
+  float2* twB = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * N;   // [a*R1 + b] = W^(a*b)
+  float* red = reinterpret_cast<float*>(sp);   sp += sizeof(float) * 64;   // [0..31] objF, [32..63] pupil partial maxima
+  float2* Pc = nullptr;
+  if constexpr (P_SMEM) { Pc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
+  float2* Qc = nullptr;                                                    // window O of this update, then Q
+  if constexpr (Q_SMEM) { Qc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
+  float* GRe = reinterpret_cast<float*>(sp);   sp += sizeof(float) * gr;   // [gr] per cell-row: max over exact cells
+  float* GRb = reinterpret_cast<float*>(sp);   sp += sizeof(float) * gr;   // [gr] per cell-row: max bound over inexact cells
+  unsigned* Tm = reinterpret_cast<unsigned*>(sp); sp += sizeof(unsigned) * tmr * tmc;   // new maxima of (cell /\ rect)
+  float* U = reinterpret_cast<float*>(sp);                                 // [gr][gc] cell maxima of |objFc|^2; sign bit set = upper bound only
+
+  float2* objFc = p.objFc + (size_t)tile * L * L;
+  float2* Pg = p.pupil + (size_t)tile * N * N;
+  float2* Qg = p.qbuf + (size_t)tile * N * N;
+  const uint16_t* __restrict__ stack = p.stack + (size_t)tile * p.n_leds * N * N;
+
+  auto Pref = [&](int iw, int jw) -> float2& {
+    if constexpr (P_SMEM) return Pc[(iw - p.ylo) * NC + (jw - p.xlo)];
+    else return Pg[(iw & (N - 1)) * N + (jw & (N - 1))];
+  };
+  auto Qref = [&](int iw, int jw) -> float2& {
+    if constexpr (Q_SMEM) return Qc[(iw - p.ylo) * NC + (jw - p.xlo)];
+    else return Qg[(iw & (N - 1)) * N + (jw & (N - 1))];
+  };
+  // Exact maxima of the two cells (cellrow, 2*seg) and (cellrow, 2*seg+1) from memory: one warp, 32 columns.
+  // Every lane of a half-warp returns its cell's maximum.
+  auto cell_pair_max = [&](int cellrow, int seg) -> float {
+    const float2* src = objFc + (size_t)(cellrow << p.cs) * L + (seg << 5) + lane;
+    float cm = 0.f;
+    for (int rr = 0; rr < (1 << p.cs); ++rr) {
+      const float2 o = src[(size_t)rr * L];
+      cm = fmaxf(cm, fmaf(o.x, o.x, o.y * o.y));
+    }
+    return half_warp_max(cm, lane);
+  };
+  // Per cell-row aggregates from U: max over exact cells, max bound over inexact ones (one warp).
+  auto row_aggregate = [&](int cellrow) {
+    float e = 0.f, b = 0.f;
+    for (int c = lane; c < gc; c += 32) {
+      const float u = U[cellrow * gc + c];
+      if (u >= 0.f) e = fmaxf(e, u); else b = fmaxf(b, -u);
+    }
+    e = warp_max(e); b = warp_max(b);
+    if (lane == 0) { GRe[cellrow] = e; GRb[cellrow] = b; }
+  };
+  // Block-wide (max exact, max bound) over all cell-rows -> red[0..NW) / red[NW..2NW)  (caller syncs)
+  auto reduce_rows = [&]() {
+    float e = 0.f, b = 0.f;
+    for (int r = tid; r < gr; r += NT) { e = fmaxf(e, GRe[r]); b = fmaxf(b, GRb[r]); }
+    e = warp_max(e); b = warp_max(b);
+    if (lane == 0) { red[warp] = e; red[NW + warp] = b; }
+  };
+
+  // ---- prologue: tables, pupil -> shared memory, max|P|^2, max-cell grid, first window ----
+  for (int t = tid; t < N; t += NT) {
+    const int b = t / R2, a = t % R2;
+    twA[t] = p.tw[a * b];
+    const int a2 = t / R1, b2 = t % R1;
+    twB[t] = p.tw[a2 * b2];
+  }
+  float pmax2 = 0.f;
+  for (int t = tid; t < NR * NC; t += NT) {
+    const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
+    const float2 v = Pg[(iw & (N - 1)) * N + (jw & (N - 1))];
+    if constexpr (P_SMEM) Pc[t] = v;
+    pmax2 = fmaxf(pmax2, fmaf(v.x, v.x, v.y * v.y));
+  }
+  pmax2 = warp_max(pmax2);
+  if (lane == 0) red[32 + warp] = pmax2;
+  for (int it = warp; it < gr * (L >> 5); it += NW) {
+    const int cellrow = it / (L >> 5), seg = it % (L >> 5);
+    const float cm = cell_pair_max(cellrow, seg);
+    if ((lane & 15) == 0) U[cellrow * gc + 2 * seg + (lane >> 4)] = cm;       // exact
+  }
+  for (int t = tid; t < tmr * tmc; t += NT) Tm[t] = 0u;
+  __syncthreads();
+  for (int cellrow = warp; cellrow < gr; cellrow += NW) row_aggregate(cellrow);
+  short2 cr_next = p.crop[p.slot_begin % p.n_leds];
+  if constexpr (Q_SMEM) {
+    const float2* w0 = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
+    for (int t = tid; t < NR * NC; t += NT) {
+      const int ir = t / NC, jc = t - ir * NC;
+      Qc[t] = w0[(p.ylo + ir) * L + p.xlo + jc];
+    }
+  }
+  __syncthreads();
+
+  const float kd1 = p.kappa * p.delta1, kd2 = p.kappa * p.delta2;
+  // psi' = a psi/|psi + eps| with psi = raw/N^2  ==  a raw/|raw + N^2 eps|: the 1/N^2 of ifft2 is never applied
+  const float epsr = p.eps * (float)(N * N), epsi = p.kappa * epsr;
+
+#ifdef FPM_STAGE_TIMING
+  long long tacc_[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tacc_[k] = 0;
+  long long tprev_ = clock64();
+#endif
+  for (int u = 0; u < p.n_updates; ++u) {
+    const int slot = (p.slot_begin + u) % p.n_leds;
+    const int xs = cr_next.x, ys = cr_next.y;
+    const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
+    cr_next = p.crop[nslot];
+    const uint16_t* __restrict__ img = stack + (size_t)slot * N * N;
+    if (tid == 0)   // pull the next LED's intensity tile towards L2 while this update runs
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(stack + (size_t)nslot * N * N), "r"((unsigned)(N * N * 2)) : "memory");
+    float2* wbase = objFc + (size_t)(ys + H) * L + (xs + H);   // absolute address of (iw=0, jw=0)
+
+    // ================= S1: Phi = O*P, cols stage A (inverse) =================
+    for (int g = tid; g < R2 * NC; g += NT) {
+      const int i0 = g / NC, jc = g - i0 * NC;
+      const int jw = p.xlo + jc, j = jw & (N - 1);
+      float2 v[R1];
+#pragma unroll
+      for (int m = 0; m < R1; ++m) {
+        const int i = i0 + R2 * m;
+        const int iw = (i < H) ? i : i - N;
+        if (iw >= p.ylo && iw <= p.yhi) {
+          float2 O;
+          if constexpr (Q_SMEM) O = Qc[(iw - p.ylo) * NC + jc]; else O = wbase[iw * L + jw];
+          v[m] = cmul(O, Pref(iw, jw));
+        } else v[m] = make_float2(0.f, 0.f);
+      }
+      fftR<R1, true>(v);
+      const int js = swz(j);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1)
+        fld[(i0 + R2 * k1) * PITCH + js] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
+    }
+    __syncthreads();
+    FPM_TICK(1);
+    // ================= S2: cols stage B (inverse) =================
+    for (int g = tid; g < R1 * NC; g += NT) {
+      const int k1 = g / NC, jc = g - k1 * NC;
+      const int js = swz((p.xlo + jc) & (N - 1));
+      float2 v[R2];
+#pragma unroll
+      for (int a = 0; a < R2; ++a) v[a] = fld[(R2 * k1 + a) * PITCH + js];
+      fftR<R2, true>(v);
+#pragma unroll
+      for (int a = 0; a < R2; ++a) fld[(R2 * k1 + a) * PITCH + js] = v[a];
+    }
+    __syncthreads();
+    FPM_TICK(2);
+    // ================= S3: rows stage A (inverse); columns outside the bbox are zero, not read =================
+    for (int g = tid; g < N * R2; g += NT) {
+      const int row = g / R2, j0 = g % R2;
+      float2* rp = fld + row * PITCH;
+      float2 v[R1];
+#pragma unroll
+      for (int m = 0; m < R1; ++m) {
+        const int col = j0 + R2 * m;
+        const int jw = (R2 * m < H) ? col : col - N;                 // R2 | H: the group does not straddle H
+        v[m] = (jw >= p.xlo && jw <= p.xhi) ? rp[swz(col)] : make_float2(0.f, 0.f);
+      }
+      fftR<R1, true>(v);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) rp[swz(j0 + R2 * k1)] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
+    }
+    __syncthreads();
+    FPM_TICK(3);
+    // ===== S4: rows stage B (inverse) + amplitude replacement + rows stage B' (forward) =====
+    for (int g = tid; g < N * R1; g += NT) {
+      const int row = g / R1, k1 = g % R1;
+      const uint4* ip = reinterpret_cast<const uint4*>(img) + (size_t)g * CH;   // permuted layout: item g owns R2 pixels
+      uint4 iv[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) iv[c] = __ldg(ip + c);
+      float2* rp = fld + row * PITCH;
+      float2 v[R2];
+#pragma unroll
+      for (int a = 0; a < R2; ++a) v[a] = rp[swz(R2 * k1 + a)];
+      fftR<R2, true>(v);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) {
+        // psi' = sqrt(I) * psi / |psi + eps|   (fpmMain.cpp:378-393), pixel x = k1 + R1*k2
+        const uint4 q4 = iv[k2 >> 3];
+        const int e2 = (k2 & 7) >> 1;
+        const uint32_t w32 = (e2 == 0) ? q4.x : (e2 == 1) ? q4.y : (e2 == 2) ? q4.z : q4.w;
+        const float inten = (float)((k2 & 1) ? (w32 >> 16) : (w32 & 0xffffu));
+        const float tx = v[k2].x + epsr, ty = v[k2].y + epsi;
+        const float sc = sqrt_fast(inten) * rsqrt_fast(fmaf(tx, tx, ty * ty));
+        v[k2] = make_float2(v[k2].x * sc, v[k2].y * sc);
+      }
+      fftR<R2, false>(v);
+#pragma unroll
+      for (int q = 0; q < R2; ++q) rp[swz(R2 * k1 + q)] = twmul<false>(v[q], twB[q * R1 + k1]);
+    }
+    __syncthreads();
+    FPM_TICK(4);
+    // ================= S5: rows stage A' (forward) =================
+    for (int g = tid; g < N * R2; g += NT) {
+      const int row = g / R2, q = g % R2;
+      float2* rp = fld + row * PITCH;
+      float2 v[R1];
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) v[k1] = rp[swz(R2 * k1 + q)];
+      fftR<R1, false>(v);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) rp[swz(R2 * r + q)] = v[r];
+    }
+    __syncthreads();
+    FPM_TICK(5);
+    // ================= S6: cols stage B' (forward) =================
+    for (int g = tid; g < R1 * NC; g += NT) {
+      const int k1 = g / NC, jc = g - k1 * NC;
+      const int js = swz((p.xlo + jc) & (N - 1));
+      float2 v[R2];
+#pragma unroll
+      for (int a = 0; a < R2; ++a) v[a] = fld[(R2 * k1 + a) * PITCH + js];
+      fftR<R2, false>(v);
+#pragma unroll
+      for (int q = 0; q < R2; ++q) fld[(R2 * k1 + q) * PITCH + js] = twmul<false>(v[q], twB[q * R1 + k1]);
+    }
+    __syncthreads();
+    FPM_TICK(6);
+    // ================= S7: cols stage A' (forward) -> Phi' in natural order =================
+    for (int g = tid; g < R2 * NC; g += NT) {
+      const int q = g / NC, jc = g - q * NC;
+      const int js = swz((p.xlo + jc) & (N - 1));
+      float2 v[R1];
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) v[k1] = fld[(R2 * k1 + q) * PITCH + js];
+      fftR<R1, false>(v);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) fld[(R2 * r + q) * PITCH + js] = v[r];
+    }
+    __syncthreads();
+    FPM_TICK(7);
+    // ===== C2: object update on the bbox (fpmMain.cpp:406-447); one warp per (row, 32-column segment) =====
+    const int r0 = ys + H + p.ylo, r1 = ys + H + p.yhi, c0 = xs + H + p.xlo, c1 = xs + H + p.xhi;   // rectangle (inclusive)
+    const int cr0 = r0 >> p.cs, ncr = (r1 >> p.cs) - cr0 + 1, cc0 = c0 >> 4, ncc = (c1 >> 4) - cc0 + 1;
+    {
+      float pm2 = red[32];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) pm2 = fmaxf(pm2, red[32 + w]);
+      const float inv_pmax = rsqrt_fast(pm2);                                  // 1 / max|P|
+      const int cbase = cc0 << 4;                          // first column of the first touched cell
+      const int npass = (ncc + 3) >> 2;                    // 64 columns (4 cells) per pass
+      for (int it = warp; it < NR * npass; it += NW) {
+        const int ir = it / npass, pass = it - ir * npass;
+        const int iw = p.ylo + ir, i = iw & (N - 1);
+        float a2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = cbase + (pass << 6) + (h << 5) + lane;
+          a2[h] = 0.f;
+          if (c >= c0 && c <= c1) {
+            const int jw = c - xs - H, j = jw & (N - 1);
+            const float sup = __ldg(p.support + i * N + j);
+            float2* gp = wbase + iw * L + jw;
+            float2 O;
+            if constexpr (Q_SMEM) O = Qref(iw, jw); else O = *gp;
+            const float2 Pv = Pref(iw, jw);
+            const float2 d = csub(fld[i * PITCH + swz(j)], cmul(O, Pv));           // dPhi = Phi' - Phi
+            // dO = d * |P| conj(P) / (max|P| * ((|P|^2 + delta2) + i*kappa*delta2))
+            const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
+            const float2 num = cmulc(d, Pv);
+            const float A = pa2 + p.delta2;
+            const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
+            const float2 On = make_float2(O.x + (num.x * A + num.y * kd2) * sc, O.y + (num.y * A - num.x * kd2) * sc);
+            *gp = On;
+            a2[h] = fmaf(On.x, On.x, On.y * On.y);
+            // Q = d * |O| conj(O) / ((|O|^2 + delta1) + i*kappa*delta1) * support   (fpmMain.cpp:459-472, O before the update)
+            const float oa2 = fmaf(O.x, O.x, O.y * O.y);
+            const float2 numq = cmulc(d, O);
+            const float A1 = oa2 + p.delta1;
+            const float sq = __fdividef(sqrt_fast(oa2) * sup, fmaf(A1, A1, kd1 * kd1));
+            Qref(iw, jw) = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
+          }
+        }
+        // new maximum of (cell /\ rectangle): a half-warp holds one 16-column cell per h
+        const int trow = (((r0 + ir) >> p.cs) - cr0) * tmc;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float m = half_warp_max(a2[h], lane);
+          const int cc = (pass << 2) + (h << 1) + (lane >> 4);
+          if ((lane & 15) == 0 && cc < ncc) atomicMax(&Tm[trow + cc], __float_as_uint(m));
+        }
+      }
+    }
+    __syncthreads();
+    FPM_TICK(8);
+    // ===== D: max|objF| (fpmMain.cpp:460,467).  Cells fully inside the rectangle are exact again; partially
+    //          covered ones keep max(old, new) as an upper bound (sign bit).  The maximum over exact cells is the
+    //          answer as soon as it dominates every bound -- otherwise E re-reads just the offending cells. =====
+    float2 wpre[2];                                  // first elements of the next LED's window, in flight across D
+    if constexpr (Q_SMEM && !(FPM_EXP & 1)) {
+      const float2* wnext = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int t = tid + k * NT;
+        if (t < NR * NC) { const int ir = t / NC; wpre[k] = wnext[(p.ylo + ir) * L + p.xlo + (t - ir * NC)]; }
+      }
+    }
+    FPM_TICK(14);
+    for (int it = warp; it < ncr; it += NW) {
+      const int cellrow = cr0 + it;
+      const bool rows_in = ((cellrow << p.cs) >= r0) && ((((cellrow + 1) << p.cs) - 1) <= r1);
+      for (int cc = lane; cc < ncc; cc += 32) {
+        const int cell = cellrow * gc + cc0 + cc;
+        const float tm = __uint_as_float(Tm[it * tmc + cc]);
+        Tm[it * tmc + cc] = 0u;
+        const bool full = rows_in && (((cc0 + cc) << 4) >= c0) && ((((cc0 + cc) << 4) + 15) <= c1);
+        U[cell] = full ? tm : -fmaxf(fabsf(U[cell]), tm);
+      }
+      __syncwarp();
+      row_aggregate(cellrow);
+    }
+    FPM_TICK(11);
+    __syncthreads();
+    FPM_TICK(12);
+    reduce_rows();
+    FPM_TICK(13);
+    __syncthreads();
+    FPM_TICK(9);
+    // ===== E: pupil update P += Q / max|objF| (fpmMain.cpp:470-475); window of the next LED -> shared memory =====
+    {
+      float om2 = red[0], bnd = red[NW];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) { om2 = fmaxf(om2, red[w]); bnd = fmaxf(bnd, red[NW + w]); }
+      if (bnd > om2) {          // rare: some partially covered cell might hold the maximum -> make those cells exact
+        __syncthreads();        // everyone has read red[]
+        for (int cellrow = warp; cellrow < gr; cellrow += NW) {
+          if (GRb[cellrow] > om2) {
+            for (int seg = 0; seg < (L >> 5); ++seg) {
+              const float u = U[cellrow * gc + 2 * seg + (lane >> 4)];
+              const bool need = (u < 0.f) && (-u > om2);
+              if (__any_sync(0xffffffffu, need)) {
+                const float cm = cell_pair_max(cellrow, seg);
+                if (need && (lane & 15) == 0) U[cellrow * gc + 2 * seg + (lane >> 4)] = cm;
+              }
+            }
+            __syncwarp();
+            row_aggregate(cellrow);
+          }
+        }
+        __syncthreads();
+        reduce_rows();
+        __syncthreads();
+        om2 = red[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) om2 = fmaxf(om2, red[w]);   // now >= every remaining bound
+      }
+      const float inv_objf_max = rsqrt_fast(om2);
+      const float2* wnext = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
+      float pnew = 0.f;
+      int k = 0;
+      for (int t = tid; t < NR * NC; t += NT, ++k) {
+        const int ir = t / NC, jc = t - ir * NC;
+        const int iw = p.ylo + ir, jw = p.xlo + jc;
+        float2 On;
+        if constexpr (Q_SMEM) On = (FPM_EXP & 1) ? wnext[iw * L + jw] : (k == 0) ? wpre[0] : (k == 1) ? wpre[1] : wnext[iw * L + jw];
+        const float2 Q = Qref(iw, jw);
+        float2& pr = Pref(iw, jw);
+        float2 v = pr;
+        v.x = fmaf(Q.x, inv_objf_max, v.x);
+        v.y = fmaf(Q.y, inv_objf_max, v.y);
+        pr = v;
+        pnew = fmaxf(pnew, fmaf(v.x, v.x, v.y * v.y));
+        if constexpr (Q_SMEM) Qc[t] = On;
+      }
+      pnew = warp_max(pnew);
+      if (lane == 0) red[32 + warp] = pnew;     // last read of red[32..] was in C2, several barriers ago
+    }
+    __syncthreads();
+    FPM_TICK(10);
+  }
+
+#ifdef FPM_STAGE_TIMING
+  if (tid == 0 && blockIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) p.stage_clk[k] += tacc_[k];
+  }
+#endif
+  if constexpr (P_SMEM) {
+    for (int t = tid; t < NR * NC; t += NT) {
+      const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
+      Pg[(iw & (N - 1)) * N + (jw & (N - 1))] = Pc[t];
+    }
+  }
+}
+
+// In-place permutation of uploaded intensity images into the device layout (one CTA per image).
+template <int N>
+__global__ void __launch_bounds__(256) stack_permute_kernel(uint16_t* stack, long long first_image) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* buf = reinterpret_cast<uint16_t*>(smem_raw);
+  uint16_t* img = stack + (size_t)(first_image + blockIdx.x) * N * N;
+  const uint4* src = reinterpret_cast<const uint4*>(img);
+  uint4* b4 = reinterpret_cast<uint4*>(buf);
+  for (int t = threadIdx.x; t < N * N / 8; t += blockDim.x) b4[t] = src[t];
+  __syncthreads();
+  for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
+    const int y = t / N, x = t % N;
+    img[stack_offset<N>(y, x)] = buf[t];
+  }
+}
+
+}  // namespace fpm

@@ -47,13 +47,14 @@ struct fpmb200_ctx {
   float2* twN = nullptr;       // [N]
   float2* twL = nullptr;       // [L]
   float2* field_gmem = nullptr;
+  float2* qbuf = nullptr;      // [n_tiles][N][N] when the pupil increment does not fit shared memory
   float2* scratch = nullptr;   // staging: max(L*L, init batch * N*N)
   size_t scratch_elems = 0;
   int ylo = 0, yhi = -1, xlo = 0, xhi = -1;
   bool have_leds = false, have_support = false, have_stack = false;
   // kernel variant
-  bool field_smem = false, p_smem = false;
-  int bs = 3;
+  bool field_smem = false, p_smem = false, q_smem = false;
+  int cs = 0;                  // log2 rows per max-cell
   size_t smem_bytes = 0;
   int max_smem_optin = 0, sm_count = 0;
   long long launches = 0;
@@ -97,8 +98,8 @@ static cudaError_t copy_sync(fpmb200_ctx* c, void* dst, const void* src, size_t 
 
 static void free_tiles(fpmb200_ctx* c) {
   cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->support);
-  cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch);
-  c->objFc = c->objCrop = c->pupil = c->twN = c->twL = c->field_gmem = c->scratch = nullptr;
+  cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch); cudaFree(c->qbuf);
+  c->objFc = c->objCrop = c->pupil = c->twN = c->twL = c->field_gmem = c->scratch = c->qbuf = nullptr;
   c->stack = nullptr; c->support = nullptr; c->crop = nullptr;
   c->have_leds = c->have_support = c->have_stack = false;
   c->n_tiles = 0;
@@ -117,7 +118,10 @@ static int upload_twiddles(fpmb200_ctx* c, float2* dst, int n) {
   std::vector<float2> h(n);
   for (int k = 0; k < n; ++k) {
     double a = -2.0 * M_PI * (double)k / (double)n;
-    h[k] = make_float2((float)cos(a), (float)sin(a));
+    double cr = cos(a), ci = sin(a);
+    if (fabs(cr) < 1e-12) cr = 0;      // exact zeros at the quarter turns
+    if (fabs(ci) < 1e-12) ci = 0;
+    h[k] = make_float2((float)cr, (float)ci);
   }
   CK(copy_sync(c, dst, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
   return FPMB200_OK;
@@ -183,14 +187,16 @@ extern "C" int fpmb200_upload_leds(fpmb200_ctx* c, const int16_t* cx, const int1
   return FPMB200_OK;
 }
 
-static size_t update_smem_bytes(const fpmb200_ctx* c, bool field_smem, bool p_smem, int bs) {
+static size_t update_smem_bytes(const fpmb200_ctx* c, bool field_smem, bool p_smem, bool q_smem, int cs) {
   const int N = c->N, PITCH = N + 8;
-  const int NR = c->yhi - c->ylo + 1, NC = c->xhi - c->xlo + 1;
+  const size_t bb = sizeof(float2) * (size_t)(c->yhi - c->ylo + 1) * (c->xhi - c->xlo + 1);
   size_t b = 0;
   if (field_smem) b += sizeof(float2) * N * PITCH;
-  if (p_smem) b += sizeof(float2) * NR * NC;
   b += sizeof(float2) * N * 2 + sizeof(float) * 64;
-  b += sizeof(float) * (size_t)(c->L >> bs) * (c->L >> bs);
+  if (p_smem) b += bb;
+  if (q_smem) b += bb;
+  b += sizeof(float) * (size_t)(c->L >> cs) * ((c->L >> 4) + 2);                     // U + GRe + GRb
+  b += sizeof(unsigned) * (size_t)(((c->yhi - c->ylo + 1) >> cs) + 2) * (((c->xhi - c->xlo + 1) >> 4) + 2);   // Tm
   return b;
 }
 
@@ -211,21 +217,34 @@ extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
   CK(cudaSetDevice(c->device));
   CK(copy_sync(c, c->support, mask, sizeof(float) * N * N, cudaMemcpyHostToDevice));
   c->have_support = true;
-  // ---- choose the kernel variant for this (N, L, bbox) ----
+  // ---- choose the kernel variant for this (N, L, bbox): what lives in shared memory ----
   const size_t cap = (size_t)c->max_smem_optin;
   c->field_smem = (N <= 128);
-  int bs = 3;
-  while (bs < 5 && sizeof(float) * (size_t)(c->L >> bs) * (c->L >> bs) > 48 * 1024) ++bs;
-  c->bs = bs;
-  c->p_smem = update_smem_bytes(c, c->field_smem, true, bs) <= cap;
-  c->smem_bytes = update_smem_bytes(c, c->field_smem, c->p_smem, bs);
-  if (c->smem_bytes > cap)
-    return fail(FPMB200_ERR_ARG, "update kernel needs %zu B shared memory, device offers %zu", c->smem_bytes, cap);
+  // what lives in shared memory: prefer pupil + pupil-increment on chip with the finest max-cells that fit
+  bool found = false;
+  for (int pq = 0; pq < 3 && !found; ++pq) {
+    const bool ps = pq < 2, qs = pq < 1;
+    for (int cs = 0; cs <= 4 && !found; ++cs) {
+      if (sizeof(float) * (size_t)(c->L >> cs) * (c->L >> 4) > 48 * 1024) continue;
+      if (update_smem_bytes(c, c->field_smem, ps, qs, cs) <= cap) {
+        c->p_smem = ps; c->q_smem = qs; c->cs = cs; found = true;
+      }
+    }
+  }
+  if (!found) return fail(FPMB200_ERR_ARG, "update kernel does not fit %zu B of shared memory (Np=%d, Nlarge=%d)", cap, N, c->L);
+  const int cs = c->cs;
+  c->smem_bytes = update_smem_bytes(c, c->field_smem, c->p_smem, c->q_smem, cs);
   if (!c->field_smem && !c->field_gmem)
     CK(cudaMalloc(&c->field_gmem, sizeof(float2) * (size_t)N * (N + 8) * c->n_tiles));
+  if (!c->q_smem && !c->qbuf) {
+    CK(cudaMalloc(&c->qbuf, sizeof(float2) * (size_t)N * N * c->n_tiles));
+    CK(cudaMemsetAsync(c->qbuf, 0, sizeof(float2) * (size_t)N * N * c->n_tiles, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
   snprintf(c->variant, sizeof c->variant,
-           "fpm_update_kernel<N=%d,field=%s,pupil=%s> bbox=[%d..%d]x[%d..%d] cell=%d smem=%zuB", N,
-           c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", ylo, yhi, xlo, xhi, 1 << bs, c->smem_bytes);
+           "fpm_update_kernel<N=%d,field=%s,pupil=%s,dP=%s> bbox=[%d..%d]x[%d..%d] maxcell=%dx16 smem=%zuB", N,
+           c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", c->q_smem ? "smem" : "gmem", ylo, yhi, xlo, xhi,
+           1 << cs, c->smem_bytes);
   return FPMB200_OK;
 }
 
@@ -245,6 +264,20 @@ extern "C" int fpmb200_upload_stack(fpmb200_ctx* c, int first, int n, const uint
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   const size_t per = (size_t)c->N * c->N * c->n_leds;
   CK(cudaMemcpyAsync(c->stack + per * first, stack, sizeof(uint16_t) * per * n, cudaMemcpyHostToDevice, st));
+  // re-order every image into the layout the update kernel streams (stack_offset<N>), in place
+  const long long first_img = (long long)first * c->n_leds;
+  const int n_img = n * c->n_leds;
+  const size_t sm = sizeof(uint16_t) * c->N * c->N;
+  switch (c->N) {
+    case 64: stack_permute_kernel<64><<<n_img, 256, sm, st>>>(c->stack, first_img); break;
+    case 128: stack_permute_kernel<128><<<n_img, 256, sm, st>>>(c->stack, first_img); break;
+    case 256:
+      CK(cudaFuncSetAttribute(stack_permute_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      stack_permute_kernel<256><<<n_img, 256, sm, st>>>(c->stack, first_img);
+      break;
+  }
+  c->launches++;
+  CK(cudaGetLastError());
   c->have_stack = true;
   return FPMB200_OK;
 }
@@ -291,7 +324,11 @@ extern "C" int fpmb200_init_tiles(fpmb200_ctx* c, int first, int n, int init_slo
   const int batch_max = (int)(c->scratch_elems / ((size_t)N * N));
   for (int t0 = first; t0 < first + n; t0 += batch_max) {
     const int b = (first + n - t0) < batch_max ? (first + n - t0) : batch_max;
-    init_amp_kernel<<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, N, c->n_leds, init_slot, t0);
+    switch (N) {
+      case 64: init_amp_kernel<64><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
+      case 128: init_amp_kernel<128><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
+      case 256: init_amp_kernel<256><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
+    }
     c->launches++;
     if ((rc = fft2d<false>(c, c->scratch, N, c->twN, b, (long long)N * N, 1.f, st))) return rc;
     init_place_kernel<<<dim3(64, b), 256, 0, st>>>(c->objFc, c->pupil, c->scratch, c->support, N, L, t0);
@@ -305,8 +342,9 @@ template <int N, int NT, int MINB>
 static int launch_update(fpmb200_ctx* c, const UpdateParams& p, int n_blocks, cudaStream_t st) {
   void (*k)(const UpdateParams) = nullptr;
   constexpr bool FS = (N <= 128);
-  if (c->p_smem) k = fpm_update_kernel<N, NT, MINB, FS, true>;
-  else k = fpm_update_kernel<N, NT, MINB, FS, false>;
+  if (c->p_smem && c->q_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, true>;
+  else if (c->p_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, false>;
+  else k = fpm_update_kernel<N, NT, MINB, FS, false, false>;
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   k<<<n_blocks, NT, c->smem_bytes, st>>>(p);
   c->launches++;
@@ -319,17 +357,17 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
   UpdateParams p;
   memset(&p, 0, sizeof p);
   p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop;
-  p.tw = c->twN; p.field_gmem = c->field_gmem; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first;
+  p.tw = c->twN; p.field_gmem = c->field_gmem; p.qbuf = c->qbuf; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first;
   p.slot_begin = slot_begin; p.n_updates = n_updates;
   p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
-  p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi; p.bs = c->bs;
+  p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi; p.cs = c->cs;
 #ifdef FPM_STAGE_TIMING
   if (!c->stage_clk) { CK(cudaMalloc(&c->stage_clk, 16 * sizeof(long long))); CK(cudaMemset(c->stage_clk, 0, 16 * sizeof(long long))); }
   p.stage_clk = c->stage_clk;
 #endif
   CK(cudaSetDevice(c->device));
   switch (c->N) {
-    case 64: return launch_update<64, 256, 3>(c, p, n, st);
+    case 64: return launch_update<64, 256, 2>(c, p, n, st);
     case 128: return launch_update<128, 512, 1>(c, p, n, st);
     case 256: return launch_update<256, 512, 1>(c, p, n, st);
   }

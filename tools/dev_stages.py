@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fpm-opencv_b200"), os.path.join(ROOT, "tests")]
 import numpy as np
 import fpmb200
-fpmb200.lib_path = lambda: os.path.join(fpmb200.LIB_DIR, "libfpmb200_timing.so")
+fpmb200.lib_path = lambda: os.path.join(fpmb200.LIB_DIR, os.environ.get("FPM_LIB", "libfpmb200_timing.so"))
 import fpm_testlib as T
 names = sys.argv[1:] or ["cfg2_fLEDc_np128"]
 for name in names:
@@ -19,9 +19,10 @@ for name in names:
         ctx.L.fpmb200_stage_clocks(ctx._h, buf)
         n_upd = 2 * len(c.cx)
         v = np.array(list(buf), dtype=np.float64) / n_upd
-        labels = ["-", "S1 colA+load", "S2 colB", "S3 rowA", "S4 rowB+amp+rowB'", "S5 rowA'", "S6 colB'", "S7 colA'", "S8 objupd+cells", "G1 reduce", "S9 pupil"]
+        labels = ["-", "S1 colA(inv)+O*P", "S2 colB(inv)", "S3 rowA(inv)", "S4 rowB+amp+rowB'", "S5 rowA'", "S6 colB'", "S7 colA'", "C2 object update", "D max|objF|", "E pupil+next window"]
         print(name, "tiles", n_tiles, ctx.variant)
         for k in range(1, 11):
             print("   %-20s %8.0f cyc  %5.1f%%" % (labels[k], v[k], 100 * v[k] / v[1:11].sum()))
-        print("   total %.0f cycles/update" % v[1:11].sum())
+        print("   total %.0f cycles/update" % v[1:16].sum())
+        print("   D detail: wpre issue %.0f | touched rows %.0f | barrier arrive->next %.0f | reduce_rows %.0f | (9)=%.0f" % (v[14], v[11], v[12], v[13], v[9]))
         ctx.close()
