@@ -90,14 +90,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 #endif
 }
+// maximum over each aligned half-warp (xor shuffles stay inside a half; a per-half REDUX mask makes the
+// compiler emit a divergence-handling loop that costs ~2k cycles per call site)
 __device__ __forceinline__ float half_warp_max(float v, int lane) {
-#if FPM_EXP & 2
+  (void)lane;
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
-#else
-  return __uint_as_float(__reduce_max_sync((lane & 16) ? 0xffff0000u : 0x0000ffffu, __float_as_uint(v)));
-#endif
 }
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -114,7 +113,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   const int L = p.L;
   const int NR = p.yhi - p.ylo + 1, NC = p.xhi - p.xlo + 1;
   const int gc = L >> 4, gr = L >> p.cs;                 // max-cells are (1<<cs) rows x 16 columns
+  const int qNT = NT / NC, rNT = NT % NC;                 // element index stepping: t += NT without dividing
   const int tmr = (NR >> p.cs) + 2, tmc = (NC >> 4) + 2;   // cells a bbox rectangle can touch
+  const int wshmax = 32 - __clz((tmc << 4) - 1);           // log2 of the padded width of the touched-cell window
 
   // ---- shared memory carve-up ----
   unsigned char* sp = smem_raw;
@@ -128,10 +129,13 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   if constexpr (P_SMEM) { Pc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
   float2* Qc = nullptr;                                                    // window O of this update, then Q
   if constexpr (Q_SMEM) { Qc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
-  float* GRe = reinterpret_cast<float*>(sp);   sp += sizeof(float) * gr;   // [gr] per cell-row: max over exact cells
-  float* GRb = reinterpret_cast<float*>(sp);   sp += sizeof(float) * gr;   // [gr] per cell-row: max bound over inexact cells
-  unsigned* Tm = reinterpret_cast<unsigned*>(sp); sp += sizeof(unsigned) * tmr * tmc;   // new maxima of (cell /\ rect)
-  float* U = reinterpret_cast<float*>(sp);                                 // [gr][gc] cell maxima of |objFc|^2; sign bit set = upper bound only
+  float* Sc = nullptr;                                                     // support on the bbox
+  if constexpr (Q_SMEM) { Sc = reinterpret_cast<float*>(sp); sp += sizeof(float) * NR * NC; }
+  unsigned* Tm = reinterpret_cast<unsigned*>(sp); sp += sizeof(unsigned) * tmr * tmc;   // new maxima of the touched cells (bit patterns)
+  float* W = nullptr;                                                      // |.|^2 of every pixel of the touched cells
+  if constexpr (Q_SMEM) { sp = smem_raw + ((size_t)(sp - smem_raw) + 15) / 16 * 16; W = reinterpret_cast<float*>(sp); sp += sizeof(float) * ((tmr << p.cs) << wshmax); }
+  sp = smem_raw + ((size_t)(sp - smem_raw) + 15) / 16 * 16;
+  float* U = reinterpret_cast<float*>(sp);                                 // [gr][gc] exact cell maxima of |objFc|^2
 
   float2* objFc = p.objFc + (size_t)tile * L * L;
   float2* Pg = p.pupil + (size_t)tile * N * N;
@@ -157,24 +161,6 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     }
     return half_warp_max(cm, lane);
   };
-  // Per cell-row aggregates from U: max over exact cells, max bound over inexact ones (one warp).
-  auto row_aggregate = [&](int cellrow) {
-    float e = 0.f, b = 0.f;
-    for (int c = lane; c < gc; c += 32) {
-      const float u = U[cellrow * gc + c];
-      if (u >= 0.f) e = fmaxf(e, u); else b = fmaxf(b, -u);
-    }
-    e = warp_max(e); b = warp_max(b);
-    if (lane == 0) { GRe[cellrow] = e; GRb[cellrow] = b; }
-  };
-  // Block-wide (max exact, max bound) over all cell-rows -> red[0..NW) / red[NW..2NW)  (caller syncs)
-  auto reduce_rows = [&]() {
-    float e = 0.f, b = 0.f;
-    for (int r = tid; r < gr; r += NT) { e = fmaxf(e, GRe[r]); b = fmaxf(b, GRb[r]); }
-    e = warp_max(e); b = warp_max(b);
-    if (lane == 0) { red[warp] = e; red[NW + warp] = b; }
-  };
-
   // ---- prologue: tables, pupil -> shared memory, max|P|^2, max-cell grid, first window ----
   for (int t = tid; t < N; t += NT) {
     const int b = t / R2, a = t % R2;
@@ -187,6 +173,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
     const float2 v = Pg[(iw & (N - 1)) * N + (jw & (N - 1))];
     if constexpr (P_SMEM) Pc[t] = v;
+    if constexpr (Q_SMEM) Sc[t] = p.support[(iw & (N - 1)) * N + (jw & (N - 1))];
     pmax2 = fmaxf(pmax2, fmaf(v.x, v.x, v.y * v.y));
   }
   pmax2 = warp_max(pmax2);
@@ -194,11 +181,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   for (int it = warp; it < gr * (L >> 5); it += NW) {
     const int cellrow = it / (L >> 5), seg = it % (L >> 5);
     const float cm = cell_pair_max(cellrow, seg);
-    if ((lane & 15) == 0) U[cellrow * gc + 2 * seg + (lane >> 4)] = cm;       // exact
+    if ((lane & 15) == 0) U[cellrow * gc + 2 * seg + (lane >> 4)] = cm;
   }
   for (int t = tid; t < tmr * tmc; t += NT) Tm[t] = 0u;
-  __syncthreads();
-  for (int cellrow = warp; cellrow < gr; cellrow += NW) row_aggregate(cellrow);
   short2 cr_next = p.crop[p.slot_begin % p.n_leds];
   if constexpr (Q_SMEM) {
     const float2* w0 = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
@@ -283,12 +268,31 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     __syncthreads();
     FPM_TICK(3);
     // ===== S4: rows stage B (inverse) + amplitude replacement + rows stage B' (forward) =====
-    for (int g = tid; g < N * R1; g += NT) {
+    constexpr int S4R = (N * R1 + NT - 1) / NT;                 // work items per thread
+    constexpr bool S4PRE = (S4R * CH <= 4);                      // all intensities up front when they fit 16 registers
+    uint4 ivall[S4PRE ? S4R : 1][CH];
+    if constexpr (S4PRE) {
+#pragma unroll
+      for (int rq = 0; rq < S4R; ++rq) {
+        const int g = tid + rq * NT;
+        if (g < N * R1) {
+          const uint4* ip = reinterpret_cast<const uint4*>(img) + (size_t)g * CH;   // permuted layout: item g owns R2 pixels
+#pragma unroll
+          for (int c = 0; c < CH; ++c) ivall[rq][c] = __ldg(ip + c);
+        }
+      }
+    }
+#pragma unroll
+    for (int rq = 0; rq < S4R; ++rq) {
+      const int g = tid + rq * NT;
+      if (g >= N * R1) break;
       const int row = g / R1, k1 = g % R1;
-      const uint4* ip = reinterpret_cast<const uint4*>(img) + (size_t)g * CH;   // permuted layout: item g owns R2 pixels
       uint4 iv[CH];
 #pragma unroll
-      for (int c = 0; c < CH; ++c) iv[c] = __ldg(ip + c);
+      for (int c = 0; c < CH; ++c) {
+        if constexpr (S4PRE) iv[c] = ivall[rq][c];
+        else iv[c] = __ldg(reinterpret_cast<const uint4*>(img) + (size_t)g * CH + c);
+      }
       float2* rp = fld + row * PITCH;
       float2 v[R2];
 #pragma unroll
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     }
     __syncthreads();
     FPM_TICK(6);
-    // ================= S7: cols stage A' (forward) -> Phi' in natural order =================
+    // ===== S7: cols stage A' (forward) -> Phi' in natural order; only bbox rows are stored (C2 reads nothing else) =====
     for (int g = tid; g < R2 * NC; g += NT) {
       const int q = g / NC, jc = g - q * NC;
       const int js = swz((p.xlo + jc) & (N - 1));
@@ -346,34 +350,59 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       for (int k1 = 0; k1 < R1; ++k1) v[k1] = fld[(R2 * k1 + q) * PITCH + js];
       fftR<R1, false>(v);
 #pragma unroll
-      for (int r = 0; r < R1; ++r) fld[(R2 * r + q) * PITCH + js] = v[r];
+      for (int r = 0; r < R1; ++r) {
+        const int i = R2 * r + q;
+        const int iw = (i < H) ? i : i - N;
+        if (iw >= p.ylo && iw <= p.yhi) fld[i * PITCH + js] = v[r];
+      }
     }
     __syncthreads();
     FPM_TICK(7);
-    // ===== C2: object update on the bbox (fpmMain.cpp:406-447); one warp per (row, 32-column segment) =====
+    // ===== C2: object update on the bbox (fpmMain.cpp:406-447), one element per thread and pass =====
     const int r0 = ys + H + p.ylo, r1 = ys + H + p.yhi, c0 = xs + H + p.xlo, c1 = xs + H + p.xhi;   // rectangle (inclusive)
     const int cr0 = r0 >> p.cs, ncr = (r1 >> p.cs) - cr0 + 1, cc0 = c0 >> 4, ncc = (c1 >> 4) - cc0 + 1;
     {
+      // Exact max|objF| bookkeeping (fpmMain.cpp:460,467): a grid U of per-cell maxima of |objFc|^2 (2^cs rows x 16
+      // columns).  The cells this rectangle touches are rebuilt in Tm by atomicMax: new values of the rectangle's
+      // pixels below, plus the pixels of those cells OUTSIDE the rectangle, which this update does not change --
+      // their loads are issued first and consumed after the element loop (one L2 latency hidden behind it).
+      const int wc0 = cc0 << 4, wcols = ncc << 4;                            // touched cells span these columns
+      const int rt0 = cr0 << p.cs, nrt = ncr << p.cs;                        // ... and these rows
+      const int wsh = 32 - __clz(wcols - 1);                                  // W rows are 2^wsh floats apart
+      const int n_out = nrt << wsh;
+      // fast path (one-row cells, everything on chip): per rectangle row the outside pixels are the left part of the
+      // first cell (lanes 0..15) and the right part of the last cell (lanes 16..31): one warp-wide load per row
+      constexpr int EPRE = 4;
+      const bool fast_edges = Q_SMEM && (p.cs == 0);
+      const int ecw = (lane < 16) ? lane : wcols - 32 + lane;
+      const bool evalid = (lane < 16) ? (wc0 + ecw < c0) : (wc0 + ecw > c1);
+      float epre[EPRE];
+      if (fast_edges) {
+#pragma unroll
+        for (int k = 0; k < EPRE; ++k) {
+          const int it = warp + k * NW;
+          epre[k] = 0.f;
+          if (it < NR && evalid) { const float2 o = objFc[(size_t)(r0 + it) * L + wc0 + ecw]; epre[k] = fmaf(o.x, o.x, o.y * o.y); }
+        }
+      }
       float pm2 = red[32];
 #pragma unroll
       for (int w = 1; w < NW; ++w) pm2 = fmaxf(pm2, red[32 + w]);
       const float inv_pmax = rsqrt_fast(pm2);                                  // 1 / max|P|
-      const int cbase = cc0 << 4;                          // first column of the first touched cell
-      const int npass = (ncc + 3) >> 2;                    // 64 columns (4 cells) per pass
-      for (int it = warp; it < NR * npass; it += NW) {
-        const int ir = it / npass, pass = it - ir * npass;
-        const int iw = p.ylo + ir, i = iw & (N - 1);
-        float a2[2];
+      const int n = NR * NC;
+      int ir = tid / NC, jc = tid - ir * NC;
+      for (int base = 0; base < n; base += 2 * NT) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = cbase + (pass << 6) + (h << 5) + lane;
-          a2[h] = 0.f;
-          if (c >= c0 && c <= c1) {
-            const int jw = c - xs - H, j = jw & (N - 1);
-            const float sup = __ldg(p.support + i * N + j);
+        for (int k = 0; k < 2; ++k) {
+          const int t = base + k * NT + tid;
+          if (t < n) {
+            const int iw = p.ylo + ir, jw = p.xlo + jc;
+            const int i = iw & (N - 1), j = jw & (N - 1);
+            float sup;
+            if constexpr (Q_SMEM) sup = Sc[t]; else sup = __ldg(p.support + i * N + j);
             float2* gp = wbase + iw * L + jw;
             float2 O;
-            if constexpr (Q_SMEM) O = Qref(iw, jw); else O = *gp;
+            if constexpr (Q_SMEM) O = Qc[t]; else O = *gp;
             const float2 Pv = Pref(iw, jw);
             const float2 d = csub(fld[i * PITCH + swz(j)], cmul(O, Pv));           // dPhi = Phi' - Phi
             // dO = d * |P| conj(P) / (max|P| * ((|P|^2 + delta2) + i*kappa*delta2))
@@ -383,7 +412,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
             const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
             const float2 On = make_float2(O.x + (num.x * A + num.y * kd2) * sc, O.y + (num.y * A - num.x * kd2) * sc);
             *gp = On;
-            a2[h] = fmaf(On.x, On.x, On.y * On.y);
+            const float a2n = fmaf(On.x, On.x, On.y * On.y);
+            if constexpr (Q_SMEM) W[((r0 + ir - rt0) << wsh) + (c0 + jc - wc0)] = a2n;
+            else atomicMax(&Tm[(((r0 + ir) >> p.cs) - cr0) * tmc + (((c0 + jc) >> 4) - cc0)], __float_as_uint(a2n));
             // Q = d * |O| conj(O) / ((|O|^2 + delta1) + i*kappa*delta1) * support   (fpmMain.cpp:459-472, O before the update)
             const float oa2 = fmaf(O.x, O.x, O.y * O.y);
             const float2 numq = cmulc(d, O);
@@ -391,89 +422,90 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
             const float sq = __fdividef(sqrt_fast(oa2) * sup, fmaf(A1, A1, kd1 * kd1));
             Qref(iw, jw) = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
           }
+          ir += qNT; jc += rNT;
+          if (jc >= NC) { jc -= NC; ++ir; }
         }
-        // new maximum of (cell /\ rectangle): a half-warp holds one 16-column cell per h
-        const int trow = (((r0 + ir) >> p.cs) - cr0) * tmc;
+      }
+      if (fast_edges) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float m = half_warp_max(a2[h], lane);
-          const int cc = (pass << 2) + (h << 1) + (lane >> 4);
-          if ((lane & 15) == 0 && cc < ncc) atomicMax(&Tm[trow + cc], __float_as_uint(m));
+        for (int k = 0; k < EPRE; ++k) {
+          const int it = warp + k * NW;
+          if (it < NR && evalid) W[(it << wsh) + ecw] = epre[k];
+        }
+        for (int it = warp + EPRE * NW; it < NR; it += NW)
+          if (evalid) { const float2 o = objFc[(size_t)(r0 + it) * L + wc0 + ecw]; W[(it << wsh) + ecw] = fmaf(o.x, o.x, o.y * o.y); }
+      } else {
+        for (int t = tid; t < n_out; t += NT) {                                  // large rectangles / multi-row cells
+          const int rr = t >> wsh, cw = t - (rr << wsh), r = rt0 + rr, c = wc0 + cw;
+          if (cw < wcols && (r < r0 || r > r1 || c < c0 || c > c1)) {
+            const float2 o = objFc[(size_t)r * L + c];
+            const float a2o = fmaf(o.x, o.x, o.y * o.y);
+            if constexpr (Q_SMEM) W[t] = a2o;
+            else atomicMax(&Tm[(rr >> p.cs) * tmc + (cw >> 4)], __float_as_uint(a2o));
+          }
         }
       }
     }
     __syncthreads();
     FPM_TICK(8);
-    // ===== D: max|objF| (fpmMain.cpp:460,467).  Cells fully inside the rectangle are exact again; partially
-    //          covered ones keep max(old, new) as an upper bound (sign bit).  The maximum over exact cells is the
-    //          answer as soon as it dominates every bound -- otherwise E re-reads just the offending cells. =====
+    // ===== D: the touched cells take their rebuilt maxima; max|objF|^2 = max over the whole grid =====
     float2 wpre[2];                                  // first elements of the next LED's window, in flight across D
-    if constexpr (Q_SMEM && !(FPM_EXP & 1)) {
+    if constexpr (Q_SMEM) {
       const float2* wnext = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
+      int ir = tid / NC, jc = tid - ir * NC;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int t = tid + k * NT;
-        if (t < NR * NC) { const int ir = t / NC; wpre[k] = wnext[(p.ylo + ir) * L + p.xlo + (t - ir * NC)]; }
+        if (tid + k * NT < NR * NC) wpre[k] = wnext[(p.ylo + ir) * L + p.xlo + jc];
+        ir += qNT; jc += rNT;
+        if (jc >= NC) { jc -= NC; ++ir; }
       }
     }
-    FPM_TICK(14);
-    for (int it = warp; it < ncr; it += NW) {
-      const int cellrow = cr0 + it;
-      const bool rows_in = ((cellrow << p.cs) >= r0) && ((((cellrow + 1) << p.cs) - 1) <= r1);
-      for (int cc = lane; cc < ncc; cc += 32) {
-        const int cell = cellrow * gc + cc0 + cc;
-        const float tm = __uint_as_float(Tm[it * tmc + cc]);
-        Tm[it * tmc + cc] = 0u;
-        const bool full = rows_in && (((cc0 + cc) << 4) >= c0) && ((((cc0 + cc) << 4) + 15) <= c1);
-        U[cell] = full ? tm : -fmaxf(fabsf(U[cell]), tm);
+    for (int t = tid; t < ncr * ncc; t += NT) {          // one thread per touched cell
+      const int a = t / ncc, b = t - a * ncc;
+      float m = 0.f;
+      if constexpr (Q_SMEM) {
+        const int wsh = 32 - __clz((ncc << 4) - 1);
+        for (int rr = a << p.cs; rr < ((a + 1) << p.cs); ++rr) {
+          const float4* w4 = reinterpret_cast<const float4*>(W + (rr << wsh) + (b << 4));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const float4 v = w4[q]; m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
+        }
+      } else {
+        m = __uint_as_float(Tm[a * tmc + b]);
+        Tm[a * tmc + b] = 0u;
       }
-      __syncwarp();
-      row_aggregate(cellrow);
+      U[(cr0 + a) * gc + cc0 + b] = m;
     }
-    FPM_TICK(11);
     __syncthreads();
-    FPM_TICK(12);
-    reduce_rows();
-    FPM_TICK(13);
+    {
+      const float4* U4 = reinterpret_cast<const float4*>(U);
+      const int n4 = (gr * gc) >> 2;                       // gc is a multiple of 4 (Nlarge multiple of 64)
+      float m = 0.f;
+      for (int base = 0; base < n4; base += 4 * NT) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int t = base + k * NT + tid;
+          if (t < n4) { const float4 q = U4[t]; m = fmaxf(fmaxf(m, fmaxf(q.x, q.y)), fmaxf(q.z, q.w)); }
+        }
+      }
+      m = warp_max(m);
+      if (lane == 0) red[warp] = m;
+    }
     __syncthreads();
     FPM_TICK(9);
     // ===== E: pupil update P += Q / max|objF| (fpmMain.cpp:470-475); window of the next LED -> shared memory =====
     {
-      float om2 = red[0], bnd = red[NW];
+      float om2 = red[0];
 #pragma unroll
-      for (int w = 1; w < NW; ++w) { om2 = fmaxf(om2, red[w]); bnd = fmaxf(bnd, red[NW + w]); }
-      if (bnd > om2) {          // rare: some partially covered cell might hold the maximum -> make those cells exact
-        __syncthreads();        // everyone has read red[]
-        for (int cellrow = warp; cellrow < gr; cellrow += NW) {
-          if (GRb[cellrow] > om2) {
-            for (int seg = 0; seg < (L >> 5); ++seg) {
-              const float u = U[cellrow * gc + 2 * seg + (lane >> 4)];
-              const bool need = (u < 0.f) && (-u > om2);
-              if (__any_sync(0xffffffffu, need)) {
-                const float cm = cell_pair_max(cellrow, seg);
-                if (need && (lane & 15) == 0) U[cellrow * gc + 2 * seg + (lane >> 4)] = cm;
-              }
-            }
-            __syncwarp();
-            row_aggregate(cellrow);
-          }
-        }
-        __syncthreads();
-        reduce_rows();
-        __syncthreads();
-        om2 = red[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) om2 = fmaxf(om2, red[w]);   // now >= every remaining bound
-      }
+      for (int w = 1; w < NW; ++w) om2 = fmaxf(om2, red[w]);
       const float inv_objf_max = rsqrt_fast(om2);
       const float2* wnext = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
       float pnew = 0.f;
-      int k = 0;
+      int ir = tid / NC, jc = tid - ir * NC, k = 0;
       for (int t = tid; t < NR * NC; t += NT, ++k) {
-        const int ir = t / NC, jc = t - ir * NC;
         const int iw = p.ylo + ir, jw = p.xlo + jc;
         float2 On;
-        if constexpr (Q_SMEM) On = (FPM_EXP & 1) ? wnext[iw * L + jw] : (k == 0) ? wpre[0] : (k == 1) ? wpre[1] : wnext[iw * L + jw];
+        if constexpr (Q_SMEM) On = (k == 0) ? wpre[0] : (k == 1) ? wpre[1] : wnext[iw * L + jw];
         const float2 Q = Qref(iw, jw);
         float2& pr = Pref(iw, jw);
         float2 v = pr;
@@ -482,6 +514,8 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
         pr = v;
         pnew = fmaxf(pnew, fmaf(v.x, v.x, v.y * v.y));
         if constexpr (Q_SMEM) Qc[t] = On;
+        ir += qNT; jc += rNT;
+        if (jc >= NC) { jc -= NC; ++ir; }
       }
       pnew = warp_max(pnew);
       if (lane == 0) red[32 + warp] = pnew;     // last read of red[32..] was in C2, several barriers ago

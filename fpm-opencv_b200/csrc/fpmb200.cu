@@ -195,8 +195,15 @@ static size_t update_smem_bytes(const fpmb200_ctx* c, bool field_smem, bool p_sm
   b += sizeof(float2) * N * 2 + sizeof(float) * 64;
   if (p_smem) b += bb;
   if (q_smem) b += bb;
-  b += sizeof(float) * (size_t)(c->L >> cs) * ((c->L >> 4) + 2);                     // U + GRe + GRb
+  b += sizeof(float) * (size_t)(c->L >> cs) * (c->L >> 4);                            // U
+  if (q_smem) b += bb / 2;                                                             // Sc (support on the bbox)
   b += sizeof(unsigned) * (size_t)(((c->yhi - c->ylo + 1) >> cs) + 2) * (((c->xhi - c->xlo + 1) >> 4) + 2);   // Tm
+  if (q_smem) {                                                                        // W: every pixel of the touched cells
+    const int tmr = ((c->yhi - c->ylo + 1) >> cs) + 2, tmc = ((c->xhi - c->xlo + 1) >> 4) + 2;
+    int wsh = 0; while ((1 << wsh) < (tmc << 4)) ++wsh;
+    b += 16 + sizeof(float) * (size_t)((tmr << cs) << wsh);
+  }
+  b += 16;                                                                             // alignment of U
   return b;
 }
 

@@ -23,6 +23,6 @@ for name in names:
         print(name, "tiles", n_tiles, ctx.variant)
         for k in range(1, 11):
             print("   %-20s %8.0f cyc  %5.1f%%" % (labels[k], v[k], 100 * v[k] / v[1:11].sum()))
-        print("   total %.0f cycles/update" % v[1:16].sum())
-        print("   D detail: wpre issue %.0f | touched rows %.0f | barrier arrive->next %.0f | reduce_rows %.0f | (9)=%.0f" % (v[14], v[11], v[12], v[13], v[9]))
+        print("   total %.0f cycles/update" % v[1:11].sum())
+        pass
         ctx.close()
