@@ -8,14 +8,51 @@
 
 namespace fpm {
 
-__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on float2.  On sm_100a the packed-fp32 pipe is used (FADD2 / FMUL2 / FFMA2 operate on a
+// 64-bit register pair; half-swap, per-half negation and scalar broadcast are operand modifiers, so a multiply by
+// -i or the (x,x)/(y,y) broadcasts of a complex product cost nothing): half the issue slots of scalar code.
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+#define FPM_PACKED 1
+#else
+#define FPM_PACKED 0
+#endif
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+#if FPM_PACKED
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
+#if FPM_PACKED
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+// a * b
 __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+#if FPM_PACKED
+  return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
+#else
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+#endif
 }
 // a * conj(b)
 __host__ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+#if FPM_PACKED
+  return __ffma2_rn(make_float2(a.x, a.x), make_float2(b.x, -b.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x)));
+#else
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+#endif
+}
+// a * s (real scale)
+__host__ __device__ __forceinline__ float2 cscale(float2 a, float s) {
+#if FPM_PACKED
+  return __fmul2_rn(a, make_float2(s, s));
+#else
+  return make_float2(a.x * s, a.y * s);
+#endif
 }
 // multiply by -i (forward quarter turn) or +i (inverse)
 template <bool INV> __host__ __device__ __forceinline__ float2 rot90(float2 a) {
@@ -69,14 +106,16 @@ template <bool INV> __host__ __device__ __forceinline__ void fft5(float2& x0, fl
   x3 = csub(p2, r);
 }
 
-// (1 -+ i)/sqrt2 and (-1 -+ i)/sqrt2 multiplications
+// (1 -+ i)/sqrt2 and (-1 -+ i)/sqrt2 multiplications: one add of a with its rotated self, one scale
 template <bool INV> __host__ __device__ __forceinline__ float2 mulW8_1(float2 a) {
   const float h = 0.70710678118654752440f;
-  return INV ? make_float2(h * (a.x - a.y), h * (a.x + a.y)) : make_float2(h * (a.x + a.y), h * (a.y - a.x));
+  // forward: h*((x+y), (y-x)) = h*(a + rot(-i)a) ; inverse: h*((x-y), (x+y)) = h*(a + rot(+i)a)
+  return cscale(cadd(a, rot90<INV>(a)), h);
 }
 template <bool INV> __host__ __device__ __forceinline__ float2 mulW8_3(float2 a) {
   const float h = 0.70710678118654752440f;
-  return INV ? make_float2(-h * (a.x + a.y), h * (a.x - a.y)) : make_float2(h * (a.y - a.x), -h * (a.x + a.y));
+  // forward: h*((y-x), -(x+y)) = h*(rot(-i)a - a) ; inverse: h*(-(x+y), (x-y)) = h*(rot(+i)a - a)
+  return cscale(csub(rot90<INV>(a), a), h);
 }
 
 template <bool INV> __host__ __device__ __forceinline__ void fft8(float2 (&v)[8]) {

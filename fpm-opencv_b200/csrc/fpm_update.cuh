@@ -60,21 +60,19 @@ struct UpdateParams {
 template <int N> struct Shape {
   static constexpr int R1 = (N == 64) ? 8 : 16;
   static constexpr int R2 = N / R1;
-  static constexpr int PITCH = N + 8;       // float2 per field row; == 8 (mod 16): row passes conflict-free
+  static constexpr int PITCH = N + 1;       // float2 per field row, odd: the 32 rows a warp touches in a row pass
+                                            // (lanes = rows, same column) land on distinct bank pairs; column passes
+                                            // (lanes = consecutive columns) are conflict-free for any pitch
   static constexpr int CH = R2 / 8;         // uint4 intensity chunks per S4 work item
 };
 
-// in-row XOR swizzle (bijective on aligned 128-blocks): lets the stride-1 radix stage (each lane owns R2
-// consecutive complex) hit 16 distinct 8-byte bank pairs per half-warp
-__host__ __device__ __forceinline__ int swz(int j) { return j ^ ((j >> 3) & 15); }
-
-// Device layout of one N x N intensity image: the R2 pixels an S4 work item needs (scrambled row
-// position p <-> spatial row y = p/R2 + R1*(p%R2); columns x = k1 + R1*k2) are contiguous.
-// Returns the uint16 offset of pixel (y, x).
+// Device layout of one N x N intensity image: S4 work item (scrambled row position p, k1) needs the R2 pixels
+// x = k1 + R1*k2 of spatial row y = p/R2 + R1*(p%R2); they are stored contiguously at item index k1*N + p, so a
+// warp (32 consecutive p, one k1) reads 32 adjacent 16-byte chunks.  Returns the uint16 offset of pixel (y, x).
 template <int N> __host__ __device__ __forceinline__ int stack_offset(int y, int x) {
   using S = Shape<N>;
   const int pos = S::R2 * (y % S::R1) + y / S::R1;
-  return (pos * S::R1 + (x % S::R1)) * S::R2 + x / S::R1;
+  return ((x % S::R1) * N + pos) * S::R2 + x / S::R1;
 }
 
 // maximum of non-negative floats over a warp: one REDUX on the bit patterns (order-preserving for v >= 0)
@@ -120,7 +118,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   // ---- shared memory carve-up ----
   unsigned char* sp = smem_raw;
   float2* fld;
-  if constexpr (FIELD_SMEM) { fld = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * N * PITCH; }
+  if constexpr (FIELD_SMEM) { fld = reinterpret_cast<float2*>(sp); sp += (sizeof(float2) * N * PITCH + 15) / 16 * 16; }
   else fld = p.field_gmem + (size_t)tile * N * PITCH;
   float2* twA = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * N;   // [b*R2 + a] = W^(a*b)
   float2* twB = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * N;   // [a*R1 + b] = W^(a*b)
@@ -230,7 +228,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
         } else v[m] = make_float2(0.f, 0.f);
       }
       fftR<R1, true>(v);
-      const int js = swz(j);
+      const int js = j;
 #pragma unroll
       for (int k1 = 0; k1 < R1; ++k1)
         fld[(i0 + R2 * k1) * PITCH + js] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     // ================= S2: cols stage B (inverse) =================
     for (int g = tid; g < R1 * NC; g += NT) {
       const int k1 = g / NC, jc = g - k1 * NC;
-      const int js = swz((p.xlo + jc) & (N - 1));
+      const int js = (p.xlo + jc) & (N - 1);
       float2 v[R2];
 #pragma unroll
       for (int a = 0; a < R2; ++a) v[a] = fld[(R2 * k1 + a) * PITCH + js];
@@ -250,20 +248,20 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     }
     __syncthreads();
     FPM_TICK(2);
-    // ================= S3: rows stage A (inverse); columns outside the bbox are zero, not read =================
+    // ===== S3: rows stage A (inverse); columns outside the bbox are zero, not read.  Lanes run over rows. =====
     for (int g = tid; g < N * R2; g += NT) {
-      const int row = g / R2, j0 = g % R2;
-      float2* rp = fld + row * PITCH;
+      const int row = g % N, j0 = g / N;
+      float2* rp = fld + row * PITCH + j0;
       float2 v[R1];
 #pragma unroll
       for (int m = 0; m < R1; ++m) {
         const int col = j0 + R2 * m;
         const int jw = (R2 * m < H) ? col : col - N;                 // R2 | H: the group does not straddle H
-        v[m] = (jw >= p.xlo && jw <= p.xhi) ? rp[swz(col)] : make_float2(0.f, 0.f);
+        v[m] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);
       }
       fftR<R1, true>(v);
 #pragma unroll
-      for (int k1 = 0; k1 < R1; ++k1) rp[swz(j0 + R2 * k1)] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
+      for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
     }
     __syncthreads();
     FPM_TICK(3);
@@ -286,17 +284,17 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     for (int rq = 0; rq < S4R; ++rq) {
       const int g = tid + rq * NT;
       if (g >= N * R1) break;
-      const int row = g / R1, k1 = g % R1;
+      const int row = g % N, k1 = g / N;
       uint4 iv[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         if constexpr (S4PRE) iv[c] = ivall[rq][c];
         else iv[c] = __ldg(reinterpret_cast<const uint4*>(img) + (size_t)g * CH + c);
       }
-      float2* rp = fld + row * PITCH;
+      float2* rp = fld + row * PITCH + R2 * k1;
       float2 v[R2];
 #pragma unroll
-      for (int a = 0; a < R2; ++a) v[a] = rp[swz(R2 * k1 + a)];
+      for (int a = 0; a < R2; ++a) v[a] = rp[a];
       fftR<R2, true>(v);
 #pragma unroll
       for (int k2 = 0; k2 < R2; ++k2) {
@@ -305,33 +303,33 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
         const int e2 = (k2 & 7) >> 1;
         const uint32_t w32 = (e2 == 0) ? q4.x : (e2 == 1) ? q4.y : (e2 == 2) ? q4.z : q4.w;
         const float inten = (float)((k2 & 1) ? (w32 >> 16) : (w32 & 0xffffu));
-        const float tx = v[k2].x + epsr, ty = v[k2].y + epsi;
-        const float sc = sqrt_fast(inten) * rsqrt_fast(fmaf(tx, tx, ty * ty));
-        v[k2] = make_float2(v[k2].x * sc, v[k2].y * sc);
+        const float2 tt = cadd(v[k2], make_float2(epsr, epsi));
+        const float sc = sqrt_fast(inten) * rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y));
+        v[k2] = cscale(v[k2], sc);
       }
       fftR<R2, false>(v);
 #pragma unroll
-      for (int q = 0; q < R2; ++q) rp[swz(R2 * k1 + q)] = twmul<false>(v[q], twB[q * R1 + k1]);
+      for (int q = 0; q < R2; ++q) rp[q] = twmul<false>(v[q], twB[q * R1 + k1]);
     }
     __syncthreads();
     FPM_TICK(4);
     // ================= S5: rows stage A' (forward) =================
     for (int g = tid; g < N * R2; g += NT) {
-      const int row = g / R2, q = g % R2;
-      float2* rp = fld + row * PITCH;
+      const int row = g % N, q = g / N;
+      float2* rp = fld + row * PITCH + q;
       float2 v[R1];
 #pragma unroll
-      for (int k1 = 0; k1 < R1; ++k1) v[k1] = rp[swz(R2 * k1 + q)];
+      for (int k1 = 0; k1 < R1; ++k1) v[k1] = rp[R2 * k1];
       fftR<R1, false>(v);
 #pragma unroll
-      for (int r = 0; r < R1; ++r) rp[swz(R2 * r + q)] = v[r];
+      for (int r = 0; r < R1; ++r) rp[R2 * r] = v[r];
     }
     __syncthreads();
     FPM_TICK(5);
     // ================= S6: cols stage B' (forward) =================
     for (int g = tid; g < R1 * NC; g += NT) {
       const int k1 = g / NC, jc = g - k1 * NC;
-      const int js = swz((p.xlo + jc) & (N - 1));
+      const int js = (p.xlo + jc) & (N - 1);
       float2 v[R2];
 #pragma unroll
       for (int a = 0; a < R2; ++a) v[a] = fld[(R2 * k1 + a) * PITCH + js];
@@ -344,7 +342,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     // ===== S7: cols stage A' (forward) -> Phi' in natural order; only bbox rows are stored (C2 reads nothing else) =====
     for (int g = tid; g < R2 * NC; g += NT) {
       const int q = g / NC, jc = g - q * NC;
-      const int js = swz((p.xlo + jc) & (N - 1));
+      const int js = (p.xlo + jc) & (N - 1);
       float2 v[R1];
 #pragma unroll
       for (int k1 = 0; k1 < R1; ++k1) v[k1] = fld[(R2 * k1 + q) * PITCH + js];
@@ -404,7 +402,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
             float2 O;
             if constexpr (Q_SMEM) O = Qc[t]; else O = *gp;
             const float2 Pv = Pref(iw, jw);
-            const float2 d = csub(fld[i * PITCH + swz(j)], cmul(O, Pv));           // dPhi = Phi' - Phi
+            const float2 d = csub(fld[i * PITCH + j], cmul(O, Pv));           // dPhi = Phi' - Phi
             // dO = d * |P| conj(P) / (max|P| * ((|P|^2 + delta2) + i*kappa*delta2))
             const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
             const float2 num = cmulc(d, Pv);

@@ -188,10 +188,10 @@ extern "C" int fpmb200_upload_leds(fpmb200_ctx* c, const int16_t* cx, const int1
 }
 
 static size_t update_smem_bytes(const fpmb200_ctx* c, bool field_smem, bool p_smem, bool q_smem, int cs) {
-  const int N = c->N, PITCH = N + 8;
+  const int N = c->N, PITCH = N + 1;
   const size_t bb = sizeof(float2) * (size_t)(c->yhi - c->ylo + 1) * (c->xhi - c->xlo + 1);
   size_t b = 0;
-  if (field_smem) b += sizeof(float2) * N * PITCH;
+  if (field_smem) b += (sizeof(float2) * N * PITCH + 15) / 16 * 16;
   b += sizeof(float2) * N * 2 + sizeof(float) * 64;
   if (p_smem) b += bb;
   if (q_smem) b += bb;
@@ -242,7 +242,7 @@ extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
   const int cs = c->cs;
   c->smem_bytes = update_smem_bytes(c, c->field_smem, c->p_smem, c->q_smem, cs);
   if (!c->field_smem && !c->field_gmem)
-    CK(cudaMalloc(&c->field_gmem, sizeof(float2) * (size_t)N * (N + 8) * c->n_tiles));
+    CK(cudaMalloc(&c->field_gmem, sizeof(float2) * (size_t)N * (N + 1) * c->n_tiles));
   if (!c->q_smem && !c->qbuf) {
     CK(cudaMalloc(&c->qbuf, sizeof(float2) * (size_t)N * N * c->n_tiles));
     CK(cudaMemsetAsync(c->qbuf, 0, sizeof(float2) * (size_t)N * N * c->n_tiles, c->stream));
