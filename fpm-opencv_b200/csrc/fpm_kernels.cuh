@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(256) line_fft_kernel(const LineFFTParams p) {
 // amplitude image of the init slot -> complex scratch [tile][N][N]   (fpmMain.cpp:319-322)
 // (the stack is in the permuted device layout of stack_offset<N>)
 template <int N>
-__global__ void init_amp_kernel(float2* scratch, const uint16_t* stack, int n_leds, int slot, int tile0) {
+__global__ void init_amp_kernel(float2* scratch, const float* stack, int n_leds, int slot, int tile0) {
   const int tile = tile0 + blockIdx.y;
-  const uint16_t* img = stack + ((size_t)tile * n_leds + slot) * N * N;
+  const float* img = stack + ((size_t)tile * n_leds + slot) * N * N;      // 1/I
   float2* out = scratch + (size_t)blockIdx.y * N * N;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N * N; t += gridDim.x * blockDim.x)
-    out[t] = make_float2(sqrtf((float)img[stack_offset<N>(t / N, t % N)]), 0.f);
+    out[t] = make_float2(sqrtf(1.0f / img[stack_offset<N>(t / N, t % N)]), 0.f);   // sqrt(I); 1/inf = 0
 }
 
 // objFc = 0; centre block <- fftShift(F * support); pupil = support   (fpmMain.cpp:312-313,326-343)

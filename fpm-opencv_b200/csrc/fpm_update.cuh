@@ -42,7 +42,7 @@ namespace fpm {
 struct UpdateParams {
   float2* objFc;            // [n_tiles][L][L]   centred spectrum
   float2* pupil;            // [n_tiles][N][N]   DC-at-corner
-  const uint16_t* stack;    // [n_tiles][n_leds][N*N] in the permuted device layout (stack_offset below)
+  const float* stack;       // [n_tiles][n_leds][N*N]: 1/intensity (inf for 0) in the permuted device layout (stack_offset)
   const float* support;     // [N][N]
   const short2* crop;       // [n_leds] (x = cropXStart, y = cropYStart)
   const float2* tw;         // [N] exp(-2*pi*i*n/N)
@@ -63,12 +63,14 @@ template <int N> struct Shape {
   static constexpr int PITCH = N + 1;       // float2 per field row, odd: the 32 rows a warp touches in a row pass
                                             // (lanes = rows, same column) land on distinct bank pairs; column passes
                                             // (lanes = consecutive columns) are conflict-free for any pitch
-  static constexpr int CH = R2 / 8;         // uint4 intensity chunks per S4 work item
+  static constexpr int CH = R2 / 4;         // float4 chunks of 1/intensity per S4 work item
 };
 
 // Device layout of one N x N intensity image: S4 work item (scrambled row position p, k1) needs the R2 pixels
 // x = k1 + R1*k2 of spatial row y = p/R2 + R1*(p%R2); they are stored contiguously at item index k1*N + p, so a
-// warp (32 consecutive p, one k1) reads 32 adjacent 16-byte chunks.  Returns the uint16 offset of pixel (y, x).
+// warp (32 consecutive p, one k1) reads 32 adjacent chunks.  Returns the element offset of pixel (y, x).
+// The device keeps 1/I as float (converted once at upload) so that the amplitude replacement
+// sqrt(I) psi/|psi+eps| = psi * rsqrt(|psi+eps|^2 / I) costs one MUFU per pixel.
 template <int N> __host__ __device__ __forceinline__ int stack_offset(int y, int x) {
   using S = Shape<N>;
   const int pos = S::R2 * (y % S::R1) + y / S::R1;
@@ -125,8 +127,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   float* red = reinterpret_cast<float*>(sp);   sp += sizeof(float) * 64;   // [0..31] objF, [32..63] pupil partial maxima
   float2* Pc = nullptr;
   if constexpr (P_SMEM) { Pc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
-  float2* Qc = nullptr;                                                    // window O of this update, then Q
-  if constexpr (Q_SMEM) { Qc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
+  float2* Qc = nullptr;                                                    // Q = pupil increment * max|objF| of the previous update
+  float2* Oc = nullptr;                                                    // window O of the current update
+  if constexpr (Q_SMEM) { Qc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; Oc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
   float* Sc = nullptr;                                                     // support on the bbox
   if constexpr (Q_SMEM) { Sc = reinterpret_cast<float*>(sp); sp += sizeof(float) * NR * NC; }
   unsigned* Tm = reinterpret_cast<unsigned*>(sp); sp += sizeof(unsigned) * tmr * tmc;   // new maxima of the touched cells (bit patterns)
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   float2* objFc = p.objFc + (size_t)tile * L * L;
   float2* Pg = p.pupil + (size_t)tile * N * N;
   float2* Qg = p.qbuf + (size_t)tile * N * N;
-  const uint16_t* __restrict__ stack = p.stack + (size_t)tile * p.n_leds * N * N;
+  const float* __restrict__ stack = p.stack + (size_t)tile * p.n_leds * N * N;
 
   auto Pref = [&](int iw, int jw) -> float2& {
     if constexpr (P_SMEM) return Pc[(iw - p.ylo) * NC + (jw - p.xlo)];
@@ -166,16 +169,13 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     const int a2 = t / R1, b2 = t % R1;
     twB[t] = p.tw[a2 * b2];
   }
-  float pmax2 = 0.f;
   for (int t = tid; t < NR * NC; t += NT) {
     const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
-    const float2 v = Pg[(iw & (N - 1)) * N + (jw & (N - 1))];
-    if constexpr (P_SMEM) Pc[t] = v;
-    if constexpr (Q_SMEM) Sc[t] = p.support[(iw & (N - 1)) * N + (jw & (N - 1))];
-    pmax2 = fmaxf(pmax2, fmaf(v.x, v.x, v.y * v.y));
+    const int gi = (iw & (N - 1)) * N + (jw & (N - 1));
+    if constexpr (P_SMEM) Pc[t] = Pg[gi];
+    if constexpr (Q_SMEM) { Sc[t] = p.support[gi]; Qc[t] = make_float2(0.f, 0.f); }
+    else Qg[gi] = make_float2(0.f, 0.f);
   }
-  pmax2 = warp_max(pmax2);
-  if (lane == 0) red[32 + warp] = pmax2;
   for (int it = warp; it < gr * (L >> 5); it += NW) {
     const int cellrow = it / (L >> 5), seg = it % (L >> 5);
     const float cm = cell_pair_max(cellrow, seg);
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     const float2* w0 = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
     for (int t = tid; t < NR * NC; t += NT) {
       const int ir = t / NC, jc = t - ir * NC;
-      Qc[t] = w0[(p.ylo + ir) * L + p.xlo + jc];
+      Oc[t] = w0[(p.ylo + ir) * L + p.xlo + jc];
     }
   }
   __syncthreads();
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   // psi' = a psi/|psi + eps| with psi = raw/N^2  ==  a raw/|raw + N^2 eps|: the 1/N^2 of ifft2 is never applied
   const float epsr = p.eps * (float)(N * N), epsi = p.kappa * epsr;
 
+  float inv_objf_max = 0.f;          // 1 / max|objF| after the previous update (its Q is still pending in Qc)
 #ifdef FPM_STAGE_TIMING
   long long tacc_[16];
 #pragma unroll
@@ -207,31 +208,43 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     const int xs = cr_next.x, ys = cr_next.y;
     const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
     cr_next = p.crop[nslot];
-    const uint16_t* __restrict__ img = stack + (size_t)slot * N * N;
+    const float* __restrict__ img = stack + (size_t)slot * N * N;
     if (tid == 0)   // pull the next LED's intensity tile towards L2 while this update runs
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(stack + (size_t)nslot * N * N), "r"((unsigned)(N * N * 2)) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(stack + (size_t)nslot * N * N), "r"((unsigned)(N * N * 4)) : "memory");
     float2* wbase = objFc + (size_t)(ys + H) * L + (xs + H);   // absolute address of (iw=0, jw=0)
 
-    // ================= S1: Phi = O*P, cols stage A (inverse) =================
-    for (int g = tid; g < R2 * NC; g += NT) {
-      const int i0 = g / NC, jc = g - i0 * NC;
-      const int jw = p.xlo + jc, j = jw & (N - 1);
-      float2 v[R1];
+    // ===== S1: pending pupil update P += Q / max|objF| (fpmMain.cpp:470-475) for the rows this thread owns, then
+    //       Phi = O*P and cols stage A (inverse).  max|P|^2 for this update's object step is reduced on the way. =====
+    {
+      float pm2 = 0.f;
+      for (int g = tid; g < R2 * NC; g += NT) {
+        const int i0 = g / NC, jc = g - i0 * NC;
+        const int jw = p.xlo + jc, j = jw & (N - 1);
+        float2 v[R1];
 #pragma unroll
-      for (int m = 0; m < R1; ++m) {
-        const int i = i0 + R2 * m;
-        const int iw = (i < H) ? i : i - N;
-        if (iw >= p.ylo && iw <= p.yhi) {
-          float2 O;
-          if constexpr (Q_SMEM) O = Qc[(iw - p.ylo) * NC + jc]; else O = wbase[iw * L + jw];
-          v[m] = cmul(O, Pref(iw, jw));
-        } else v[m] = make_float2(0.f, 0.f);
+        for (int m = 0; m < R1; ++m) {
+          const int i = i0 + R2 * m;
+          const int iw = (i < H) ? i : i - N;
+          if (iw >= p.ylo && iw <= p.yhi) {
+            float2 O;
+            if constexpr (Q_SMEM) O = Oc[(iw - p.ylo) * NC + jc]; else O = wbase[iw * L + jw];
+            const float2 Q = Qref(iw, jw);
+            float2& pr = Pref(iw, jw);
+            float2 Pv = pr;
+            Pv.x = fmaf(Q.x, inv_objf_max, Pv.x);
+            Pv.y = fmaf(Q.y, inv_objf_max, Pv.y);
+            pr = Pv;
+            pm2 = fmaxf(pm2, fmaf(Pv.x, Pv.x, Pv.y * Pv.y));
+            v[m] = cmul(O, Pv);
+          } else v[m] = make_float2(0.f, 0.f);
+        }
+        fftR<R1, true>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1)
+          fld[(i0 + R2 * k1) * PITCH + j] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
       }
-      fftR<R1, true>(v);
-      const int js = j;
-#pragma unroll
-      for (int k1 = 0; k1 < R1; ++k1)
-        fld[(i0 + R2 * k1) * PITCH + js] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
+      pm2 = warp_max(pm2);
+      if (lane == 0) red[32 + warp] = pm2;
     }
     __syncthreads();
     FPM_TICK(1);
@@ -267,14 +280,14 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     FPM_TICK(3);
     // ===== S4: rows stage B (inverse) + amplitude replacement + rows stage B' (forward) =====
     constexpr int S4R = (N * R1 + NT - 1) / NT;                 // work items per thread
-    constexpr bool S4PRE = (S4R * CH <= 4);                      // all intensities up front when they fit 16 registers
-    uint4 ivall[S4PRE ? S4R : 1][CH];
+    constexpr bool S4PRE = (S4R * CH <= 8);                      // all 1/I up front when they fit 32 registers
+    float4 ivall[S4PRE ? S4R : 1][CH];
     if constexpr (S4PRE) {
 #pragma unroll
       for (int rq = 0; rq < S4R; ++rq) {
         const int g = tid + rq * NT;
         if (g < N * R1) {
-          const uint4* ip = reinterpret_cast<const uint4*>(img) + (size_t)g * CH;   // permuted layout: item g owns R2 pixels
+          const float4* ip = reinterpret_cast<const float4*>(img) + (size_t)g * CH;   // permuted layout: item g owns R2 pixels
 #pragma unroll
           for (int c = 0; c < CH; ++c) ivall[rq][c] = __ldg(ip + c);
         }
@@ -285,11 +298,11 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       const int g = tid + rq * NT;
       if (g >= N * R1) break;
       const int row = g % N, k1 = g / N;
-      uint4 iv[CH];
+      float4 iv[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         if constexpr (S4PRE) iv[c] = ivall[rq][c];
-        else iv[c] = __ldg(reinterpret_cast<const uint4*>(img) + (size_t)g * CH + c);
+        else iv[c] = __ldg(reinterpret_cast<const float4*>(img) + (size_t)g * CH + c);
       }
       float2* rp = fld + row * PITCH + R2 * k1;
       float2 v[R2];
@@ -298,13 +311,12 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       fftR<R2, true>(v);
 #pragma unroll
       for (int k2 = 0; k2 < R2; ++k2) {
-        // psi' = sqrt(I) * psi / |psi + eps|   (fpmMain.cpp:378-393), pixel x = k1 + R1*k2
-        const uint4 q4 = iv[k2 >> 3];
-        const int e2 = (k2 & 7) >> 1;
-        const uint32_t w32 = (e2 == 0) ? q4.x : (e2 == 1) ? q4.y : (e2 == 2) ? q4.z : q4.w;
-        const float inten = (float)((k2 & 1) ? (w32 >> 16) : (w32 & 0xffffu));
+        // psi' = sqrt(I) * psi / |psi + eps| = psi * rsqrt(|psi + eps|^2 / I)   (fpmMain.cpp:378-393), pixel x = k1 + R1*k2
+        const float4 q4 = iv[k2 >> 2];
+        const int e = k2 & 3;
+        const float inv_i = (e == 0) ? q4.x : (e == 1) ? q4.y : (e == 2) ? q4.z : q4.w;
         const float2 tt = cadd(v[k2], make_float2(epsr, epsi));
-        const float sc = sqrt_fast(inten) * rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y));
+        const float sc = rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y) * inv_i);
         v[k2] = cscale(v[k2], sc);
       }
       fftR<R2, false>(v);
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
             if constexpr (Q_SMEM) sup = Sc[t]; else sup = __ldg(p.support + i * N + j);
             float2* gp = wbase + iw * L + jw;
             float2 O;
-            if constexpr (Q_SMEM) O = Qc[t]; else O = *gp;
+            if constexpr (Q_SMEM) O = Oc[t]; else O = *gp;
             const float2 Pv = Pref(iw, jw);
             const float2 d = csub(fld[i * PITCH + j], cmul(O, Pv));           // dPhi = Phi' - Phi
             // dO = d * |P| conj(P) / (max|P| * ((|P|^2 + delta2) + i*kappa*delta2))
@@ -489,36 +501,23 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       m = warp_max(m);
       if (lane == 0) red[warp] = m;
     }
+    if constexpr (Q_SMEM) {                           // window of the next LED -> shared memory (C2 is done with Oc)
+      const float2* wnext = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
+      int ir = tid / NC, jc = tid - ir * NC, k = 0;
+      for (int t = tid; t < NR * NC; t += NT, ++k) {
+        Oc[t] = (k == 0) ? wpre[0] : (k == 1) ? wpre[1] : wnext[(p.ylo + ir) * L + p.xlo + jc];
+        ir += qNT; jc += rNT;
+        if (jc >= NC) { jc -= NC; ++ir; }
+      }
+    }
     __syncthreads();
     FPM_TICK(9);
-    // ===== E: pupil update P += Q / max|objF| (fpmMain.cpp:470-475); window of the next LED -> shared memory =====
     {
       float om2 = red[0];
 #pragma unroll
       for (int w = 1; w < NW; ++w) om2 = fmaxf(om2, red[w]);
-      const float inv_objf_max = rsqrt_fast(om2);
-      const float2* wnext = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
-      float pnew = 0.f;
-      int ir = tid / NC, jc = tid - ir * NC, k = 0;
-      for (int t = tid; t < NR * NC; t += NT, ++k) {
-        const int iw = p.ylo + ir, jw = p.xlo + jc;
-        float2 On;
-        if constexpr (Q_SMEM) On = (k == 0) ? wpre[0] : (k == 1) ? wpre[1] : wnext[iw * L + jw];
-        const float2 Q = Qref(iw, jw);
-        float2& pr = Pref(iw, jw);
-        float2 v = pr;
-        v.x = fmaf(Q.x, inv_objf_max, v.x);
-        v.y = fmaf(Q.y, inv_objf_max, v.y);
-        pr = v;
-        pnew = fmaxf(pnew, fmaf(v.x, v.x, v.y * v.y));
-        if constexpr (Q_SMEM) Qc[t] = On;
-        ir += qNT; jc += rNT;
-        if (jc >= NC) { jc -= NC; ++ir; }
-      }
-      pnew = warp_max(pnew);
-      if (lane == 0) red[32 + warp] = pnew;     // last read of red[32..] was in C2, several barriers ago
+      inv_objf_max = rsqrt_fast(om2);                // applied to P by the next S1 (or by the epilogue below)
     }
-    __syncthreads();
     FPM_TICK(10);
   }
 
@@ -528,6 +527,17 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     for (int k = 0; k < 16; ++k) p.stage_clk[k] += tacc_[k];
   }
 #endif
+  // the last update's pupil increment is still pending
+  for (int t = tid; t < NR * NC; t += NT) {
+    const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
+    const float2 Q = Qref(iw, jw);
+    float2& pr = Pref(iw, jw);
+    float2 v = pr;
+    v.x = fmaf(Q.x, inv_objf_max, v.x);
+    v.y = fmaf(Q.y, inv_objf_max, v.y);
+    pr = v;
+  }
+  __syncthreads();
   if constexpr (P_SMEM) {
     for (int t = tid; t < NR * NC; t += NT) {
       const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
@@ -536,19 +546,14 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   }
 }
 
-// In-place permutation of uploaded intensity images into the device layout (one CTA per image).
+// Uploaded uint16 images -> 1/I as float in the device layout (one CTA per image; runs once per upload).
 template <int N>
-__global__ void __launch_bounds__(256) stack_permute_kernel(uint16_t* stack, long long first_image) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint16_t* buf = reinterpret_cast<uint16_t*>(smem_raw);
-  uint16_t* img = stack + (size_t)(first_image + blockIdx.x) * N * N;
-  const uint4* src = reinterpret_cast<const uint4*>(img);
-  uint4* b4 = reinterpret_cast<uint4*>(buf);
-  for (int t = threadIdx.x; t < N * N / 8; t += blockDim.x) b4[t] = src[t];
-  __syncthreads();
+__global__ void __launch_bounds__(256) stack_convert_kernel(float* stack, const uint16_t* raw, long long first_image) {
+  const uint16_t* src = raw + (size_t)(first_image + blockIdx.x) * N * N;
+  float* dst = stack + (size_t)(first_image + blockIdx.x) * N * N;
   for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
     const int y = t / N, x = t % N;
-    img[stack_offset<N>(y, x)] = buf[t];
+    dst[stack_offset<N>(y, x)] = 1.0f / (float)src[t];       // 0 -> +inf: rsqrt(inf) = 0 = sqrt(0)
   }
 }
 

@@ -41,7 +41,8 @@ struct fpmb200_ctx {
   float2* objFc = nullptr;     // [n_tiles][L][L] centred
   float2* objCrop = nullptr;   // [n_tiles][L][L]
   float2* pupil = nullptr;     // [n_tiles][N][N]
-  uint16_t* stack = nullptr;   // [n_tiles][n_leds][N][N]
+  float* stack = nullptr;      // [n_tiles][n_leds][N*N] 1/I in the kernel's layout
+  uint16_t* raw = nullptr;     // [n_tiles][n_leds][N][N] upload staging (as given by the host)
   float* support = nullptr;    // [N][N]
   short2* crop = nullptr;      // [n_leds]
   float2* twN = nullptr;       // [N]
@@ -97,10 +98,10 @@ static cudaError_t copy_sync(fpmb200_ctx* c, void* dst, const void* src, size_t 
 }
 
 static void free_tiles(fpmb200_ctx* c) {
-  cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->support);
+  cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->raw); cudaFree(c->support);
   cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch); cudaFree(c->qbuf);
   c->objFc = c->objCrop = c->pupil = c->twN = c->twL = c->field_gmem = c->scratch = c->qbuf = nullptr;
-  c->stack = nullptr; c->support = nullptr; c->crop = nullptr;
+  c->stack = nullptr; c->raw = nullptr; c->support = nullptr; c->crop = nullptr;
   c->have_leds = c->have_support = c->have_stack = false;
   c->n_tiles = 0;
 }
@@ -146,7 +147,8 @@ extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlar
   CK(cudaMalloc(&c->objFc, sizeof(float2) * LL * n_tiles));
   CK(cudaMalloc(&c->objCrop, sizeof(float2) * LL * n_tiles));
   CK(cudaMalloc(&c->pupil, sizeof(float2) * NN * n_tiles));
-  CK(cudaMalloc(&c->stack, sizeof(uint16_t) * NN * n_leds * n_tiles));
+  CK(cudaMalloc(&c->stack, sizeof(float) * NN * n_leds * n_tiles));
+  CK(cudaMalloc(&c->raw, sizeof(uint16_t) * NN * n_leds * n_tiles));
   CK(cudaMalloc(&c->support, sizeof(float) * NN));
   CK(cudaMalloc(&c->crop, sizeof(short2) * n_leds));
   CK(cudaMalloc(&c->twN, sizeof(float2) * Np));
@@ -194,7 +196,7 @@ static size_t update_smem_bytes(const fpmb200_ctx* c, bool field_smem, bool p_sm
   if (field_smem) b += (sizeof(float2) * N * PITCH + 15) / 16 * 16;
   b += sizeof(float2) * N * 2 + sizeof(float) * 64;
   if (p_smem) b += bb;
-  if (q_smem) b += bb;
+  if (q_smem) b += 2 * bb;                                                             // Qc + Oc
   b += sizeof(float) * (size_t)(c->L >> cs) * (c->L >> 4);                            // U
   if (q_smem) b += bb / 2;                                                             // Sc (support on the bbox)
   b += sizeof(unsigned) * (size_t)(((c->yhi - c->ylo + 1) >> cs) + 2) * (((c->xhi - c->xlo + 1) >> 4) + 2);   // Tm
@@ -270,18 +272,14 @@ extern "C" int fpmb200_upload_stack(fpmb200_ctx* c, int first, int n, const uint
   CK(cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   const size_t per = (size_t)c->N * c->N * c->n_leds;
-  CK(cudaMemcpyAsync(c->stack + per * first, stack, sizeof(uint16_t) * per * n, cudaMemcpyHostToDevice, st));
-  // re-order every image into the layout the update kernel streams (stack_offset<N>), in place
+  CK(cudaMemcpyAsync(c->raw + per * first, stack, sizeof(uint16_t) * per * n, cudaMemcpyHostToDevice, st));
+  // once per upload: uint16 -> 1/I (float) in the layout the update kernel streams (stack_offset<N>)
   const long long first_img = (long long)first * c->n_leds;
   const int n_img = n * c->n_leds;
-  const size_t sm = sizeof(uint16_t) * c->N * c->N;
   switch (c->N) {
-    case 64: stack_permute_kernel<64><<<n_img, 256, sm, st>>>(c->stack, first_img); break;
-    case 128: stack_permute_kernel<128><<<n_img, 256, sm, st>>>(c->stack, first_img); break;
-    case 256:
-      CK(cudaFuncSetAttribute(stack_permute_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      stack_permute_kernel<256><<<n_img, 256, sm, st>>>(c->stack, first_img);
-      break;
+    case 64: stack_convert_kernel<64><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
+    case 128: stack_convert_kernel<128><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
+    case 256: stack_convert_kernel<256><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
   }
   c->launches++;
   CK(cudaGetLastError());
@@ -463,7 +461,7 @@ extern "C" int fpmb200_device_buffer(fpmb200_ctx* c, int which, int tile, void**
     case 0: b = sizeof(float2) * LL; *ptr = c->objFc + LL * tile; break;
     case 1: b = sizeof(float2) * LL; *ptr = c->objCrop + LL * tile; break;
     case 2: b = sizeof(float2) * NN; *ptr = c->pupil + NN * tile; break;
-    case 3: b = sizeof(uint16_t) * NN * c->n_leds; *ptr = c->stack + NN * c->n_leds * tile; break;
+    case 3: b = sizeof(float) * NN * c->n_leds; *ptr = c->stack + NN * c->n_leds * tile; break;
     default: return fail(FPMB200_ERR_ARG, "which=%d not in 0..3", which);
   }
   if (bytes) *bytes = b;

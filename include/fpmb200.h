@@ -91,7 +91,8 @@ int fpmb200_download_objcrop(fpmb200_ctx* ctx, int tile_first, int n, float* obj
 
 /* Device pointer of tile `tile`'s buffer for zero-copy hand-off (e.g. the final NCCL gather of a
  * multi-GPU run): which = 0 centred spectrum [Nlarge][Nlarge][2] float, 1 objCrop, 2 pupil,
- * 3 intensity stack (uint16).  Consecutive tiles are contiguous. */
+ * 3 intensity stack as the kernel keeps it (float 1/I in the permuted layout of csrc/fpm_update.cuh
+ * `stack_offset`).  Consecutive tiles are contiguous. */
 int fpmb200_device_buffer(fpmb200_ctx* ctx, int which, int tile, void** ptr, unsigned long long* bytes_per_tile);
 
 int fpmb200_sync(fpmb200_ctx* ctx);
