@@ -27,6 +27,7 @@
 //       warp per touched cell-row refreshes its cells and the row maximum; untouched rows are reused
 //   E   P += Q / max|objF| (fpmMain.cpp:459-475), max|P| and the window of the next LED
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "fft_regs.cuh"
@@ -40,6 +41,7 @@
 namespace fpm {
 
 struct UpdateParams {
+  CUtensorMap tmap;         // objFc as a 3-D float tensor (2*L, L, n_tiles); box = (2*ocp, NR, 1): one TMA = one bbox window
   float2* objFc;            // [n_tiles][L][L]   centred spectrum
   float2* pupil;            // [n_tiles][N][N]   DC-at-corner
   const float* stack;       // [n_tiles][n_leds][N*N]: 1/intensity (inf for 0) in the permuted device layout (stack_offset)
@@ -53,6 +55,7 @@ struct UpdateParams {
   int slot_begin, n_updates;
   float delta1, delta2, eps, kappa;
   int ylo, yhi, xlo, xhi;   // support bbox (wrapped)
+  int ocp;                  // row pitch (float2) of the on-chip window copies: even and >= NC+1 (TMA boxes start on 16 B)
   int cs;                   // log2 rows per max-cell (cells are (1<<cs) rows x 32 columns)
   long long* stage_clk;     // [16] per-stage cycle totals of CTA 0 (only with -DFPM_STAGE_TIMING)
 };
@@ -101,12 +104,51 @@ __device__ __forceinline__ float half_warp_max(float v, int lane) {
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+#if FPM_EXP & 16
+  bytes = 0;
+#endif
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one 3-D box (x = float index in the row, y = row, z = tile) global -> shared, completion on `bar`
+__device__ __forceinline__ void tma_load_window(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+#if FPM_EXP & 16
+  (void)dst; (void)map; (void)x; (void)y; (void)z; (void)bar; return;
+#endif
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// one 3-D box shared -> global (bulk async group)
+__device__ __forceinline__ void tma_store_window(const void* src, const CUtensorMap* map, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int N, int NT, int MINB, bool FIELD_SMEM, bool P_SMEM, bool Q_SMEM>
-__global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams p) {
+__global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_constant__ UpdateParams p) {
   using S = Shape<N>;
   constexpr int R1 = S::R1, R2 = S::R2, PITCH = S::PITCH, CH = S::CH;
   constexpr int H = N / 2, NW = NT / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];   // TMA destinations need 128-byte alignment
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = p.tile0 + blockIdx.x;
@@ -128,8 +170,16 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
   float2* Pc = nullptr;
   if constexpr (P_SMEM) { Pc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
   float2* Qc = nullptr;                                                    // Q = pupil increment * max|objF| of the previous update
-  float2* Oc = nullptr;                                                    // window O of the current update
-  if constexpr (Q_SMEM) { Qc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; Oc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
+  float2* Ocb[2] = {nullptr, nullptr};                                     // windows O of this and the next update (TMA destinations)
+  const int OCP = p.ocp;
+  if constexpr (Q_SMEM) {
+    Qc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC;
+    sp += (128u - (smem_u32(sp) & 127u)) & 127u;          // absolute 128-byte alignment (the dynamic base is only 16-aligned)
+    Ocb[0] = reinterpret_cast<float2*>(sp); sp += ((sizeof(float2) * NR * OCP + 127) / 128) * 128;
+    Ocb[1] = reinterpret_cast<float2*>(sp); sp += ((sizeof(float2) * NR * OCP + 127) / 128) * 128;
+  }
+  __shared__ __align__(8) uint64_t wbar;                                   // completion barrier of the window TMA
+  const uint32_t win_bytes = (uint32_t)(sizeof(float2) * NR * OCP);
   float* Sc = nullptr;                                                     // support on the bbox
   if constexpr (Q_SMEM) { Sc = reinterpret_cast<float*>(sp); sp += sizeof(float) * NR * NC; }
   unsigned* Tm = reinterpret_cast<unsigned*>(sp); sp += sizeof(unsigned) * tmr * tmc;   // new maxima of the touched cells (bit patterns)
@@ -182,12 +232,17 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     if ((lane & 15) == 0) U[cellrow * gc + 2 * seg + (lane >> 4)] = cm;
   }
   for (int t = tid; t < tmr * tmc; t += NT) Tm[t] = 0u;
-  short2 cr_next = p.crop[p.slot_begin % p.n_leds];
+  // crop origins of this update, the next and the one after (windows are fetched one update ahead)
+  short2 cr_a = p.crop[p.slot_begin % p.n_leds], cr_b = p.crop[(p.slot_begin + 1) % p.n_leds];
+  uint32_t wphase = 0;
   if constexpr (Q_SMEM) {
-    const float2* w0 = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
-    for (int t = tid; t < NR * NC; t += NT) {
-      const int ir = t / NC, jc = t - ir * NC;
-      Oc[t] = w0[(p.ylo + ir) * L + p.xlo + jc];
+    if (tid == 0) {
+      mbar_init(&wbar, 1);
+      asm volatile("fence.proxy.async;" ::: "memory");
+      mbar_expect_tx(&wbar, 2 * win_bytes);
+      // TMA box starts must be 16-byte aligned: fetch from the even column at or left of the window (ocp has room)
+      tma_load_window(Ocb[0], &p.tmap, 2 * ((cr_a.x + H + p.xlo) & ~1), cr_a.y + H + p.ylo, tile, &wbar);
+      tma_load_window(Ocb[1], &p.tmap, 2 * ((cr_b.x + H + p.xlo) & ~1), cr_b.y + H + p.ylo, tile, &wbar);
     }
   }
   __syncthreads();
@@ -205,9 +260,13 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
 #endif
   for (int u = 0; u < p.n_updates; ++u) {
     const int slot = (p.slot_begin + u) % p.n_leds;
-    const int xs = cr_next.x, ys = cr_next.y;
+    const int xs = cr_a.x, ys = cr_a.y;
     const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
-    cr_next = p.crop[nslot];
+    const int nslot2 = (nslot + 1 == p.n_leds) ? 0 : nslot + 1;
+    const short2 cr_c = p.crop[nslot2];
+    float2* Oc = Ocb[u & 1] + ((xs + H + p.xlo) & 1);              // window element (ir, jc) = Oc[ir*OCP + jc]
+    float2* Ocn = Ocb[(u & 1) ^ 1];                                // next window's box, box-relative columns
+    if constexpr (Q_SMEM) { if (u == 0) { mbar_wait(&wbar, wphase); wphase ^= 1; } }
     const float* __restrict__ img = stack + (size_t)slot * N * N;
     if (tid == 0)   // pull the next LED's intensity tile towards L2 while this update runs
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(stack + (size_t)nslot * N * N), "r"((unsigned)(N * N * 4)) : "memory");
@@ -227,7 +286,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
           const int iw = (i < H) ? i : i - N;
           if (iw >= p.ylo && iw <= p.yhi) {
             float2 O;
-            if constexpr (Q_SMEM) O = Oc[(iw - p.ylo) * NC + jc]; else O = wbase[iw * L + jw];
+            if constexpr (Q_SMEM) O = Oc[(iw - p.ylo) * OCP + jc]; else O = wbase[iw * L + jw];
             const float2 Q = Qref(iw, jw);
             float2& pr = Pref(iw, jw);
             float2 Pv = pr;
@@ -261,6 +320,16 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     }
     __syncthreads();
     FPM_TICK(2);
+    if constexpr (Q_SMEM) {
+      // Window of update u+1 -> the buffer update u-1 released.  Its TMA store was issued a third of an update ago, so
+      // the wait is free; the load has until C2 (which forwards this update's values into it) to land.
+      if (tid == 0 && u > 0) {
+        tma_store_wait_all();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(&wbar, win_bytes);
+        tma_load_window(Ocn, &p.tmap, 2 * ((cr_b.x + H + p.xlo) & ~1), cr_b.y + H + p.ylo, tile, &wbar);
+      }
+    }
     // ===== S3: rows stage A (inverse); columns outside the bbox are zero, not read.  Lanes run over rows. =====
     for (int g = tid; g < N * R2; g += NT) {
       const int row = g % N, j0 = g / N;
@@ -371,11 +440,15 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     // ===== C2: object update on the bbox (fpmMain.cpp:406-447), one element per thread and pass =====
     const int r0 = ys + H + p.ylo, r1 = ys + H + p.yhi, c0 = xs + H + p.xlo, c1 = xs + H + p.xhi;   // rectangle (inclusive)
     const int cr0 = r0 >> p.cs, ncr = (r1 >> p.cs) - cr0 + 1, cc0 = c0 >> 4, ncc = (c1 >> 4) - cc0 + 1;
+    // the next LED's window was fetched by TMA before this update's writes: wait for it, then patch the overlap
+    const int r0n = cr_b.y + H + p.ylo, c0n = (cr_b.x + H + p.xlo) & ~1;   // origin of the next window's TMA box
+    if constexpr (Q_SMEM) { if (u > 0) { mbar_wait(&wbar, wphase); wphase ^= 1; } }
     {
       // Exact max|objF| bookkeeping (fpmMain.cpp:460,467): a grid U of per-cell maxima of |objFc|^2 (2^cs rows x 16
       // columns).  The cells this rectangle touches are rebuilt in Tm by atomicMax: new values of the rectangle's
       // pixels below, plus the pixels of those cells OUTSIDE the rectangle, which this update does not change --
-      // their loads are issued first and consumed after the element loop (one L2 latency hidden behind it).
+      // their loads are issued first and consumed after the element loop (one L2 latency hidden behind it).  They read
+      // L2 (ld.cg): earlier windows were written back by TMA stores, which do not update this SM's L1.
       const int wc0 = cc0 << 4, wcols = ncc << 4;                            // touched cells span these columns
       const int rt0 = cr0 << p.cs, nrt = ncr << p.cs;                        // ... and these rows
       const int wsh = 32 - __clz(wcols - 1);                                  // W rows are 2^wsh floats apart
@@ -392,7 +465,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
         for (int k = 0; k < EPRE; ++k) {
           const int it = warp + k * NW;
           epre[k] = 0.f;
-          if (it < NR && evalid) { const float2 o = objFc[(size_t)(r0 + it) * L + wc0 + ecw]; epre[k] = fmaf(o.x, o.x, o.y * o.y); }
+          if (it < NR && evalid) { const float2 o = __ldcg(objFc + (size_t)(r0 + it) * L + wc0 + ecw); epre[k] = fmaf(o.x, o.x, o.y * o.y); }
         }
       }
       float pm2 = red[32];
@@ -412,7 +485,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
             if constexpr (Q_SMEM) sup = Sc[t]; else sup = __ldg(p.support + i * N + j);
             float2* gp = wbase + iw * L + jw;
             float2 O;
-            if constexpr (Q_SMEM) O = Oc[t]; else O = *gp;
+            if constexpr (Q_SMEM) O = Oc[ir * OCP + jc]; else O = *gp;
             const float2 Pv = Pref(iw, jw);
             const float2 d = csub(fld[i * PITCH + j], cmul(O, Pv));           // dPhi = Phi' - Phi
             // dO = d * |P| conj(P) / (max|P| * ((|P|^2 + delta2) + i*kappa*delta2))
@@ -421,7 +494,14 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
             const float A = pa2 + p.delta2;
             const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
             const float2 On = make_float2(O.x + (num.x * A + num.y * kd2) * sc, O.y + (num.y * A - num.x * kd2) * sc);
-            *gp = On;
+            if constexpr (Q_SMEM) {
+              Oc[ir * OCP + jc] = On;        // the whole box goes back to the spectrum with one TMA store after the barrier
+              // forward the new value into the next window's box where the two overlap (the box was fetched earlier)
+              const int rn = r0 + ir - r0n, cn = c0 + jc - c0n;
+              if ((unsigned)rn < (unsigned)NR && (unsigned)cn < (unsigned)OCP) Ocn[rn * OCP + cn] = On;
+            } else {
+              *gp = On;
+            }
             const float a2n = fmaf(On.x, On.x, On.y * On.y);
             if constexpr (Q_SMEM) W[((r0 + ir - rt0) << wsh) + (c0 + jc - wc0)] = a2n;
             else atomicMax(&Tm[(((r0 + ir) >> p.cs) - cr0) * tmc + (((c0 + jc) >> 4) - cc0)], __float_as_uint(a2n));
@@ -443,12 +523,12 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
           if (it < NR && evalid) W[(it << wsh) + ecw] = epre[k];
         }
         for (int it = warp + EPRE * NW; it < NR; it += NW)
-          if (evalid) { const float2 o = objFc[(size_t)(r0 + it) * L + wc0 + ecw]; W[(it << wsh) + ecw] = fmaf(o.x, o.x, o.y * o.y); }
+          if (evalid) { const float2 o = __ldcg(objFc + (size_t)(r0 + it) * L + wc0 + ecw); W[(it << wsh) + ecw] = fmaf(o.x, o.x, o.y * o.y); }
       } else {
         for (int t = tid; t < n_out; t += NT) {                                  // large rectangles / multi-row cells
           const int rr = t >> wsh, cw = t - (rr << wsh), r = rt0 + rr, c = wc0 + cw;
           if (cw < wcols && (r < r0 || r > r1 || c < c0 || c > c1)) {
-            const float2 o = objFc[(size_t)r * L + c];
+            const float2 o = __ldcg(objFc + (size_t)r * L + c);
             const float a2o = fmaf(o.x, o.x, o.y * o.y);
             if constexpr (Q_SMEM) W[t] = a2o;
             else atomicMax(&Tm[(rr >> p.cs) * tmc + (cw >> 4)], __float_as_uint(a2o));
@@ -456,20 +536,13 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
         }
       }
     }
+    if constexpr (Q_SMEM) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // Oc writes -> visible to the TMA store
     __syncthreads();
     FPM_TICK(8);
-    // ===== D: the touched cells take their rebuilt maxima; max|objF|^2 = max over the whole grid =====
-    float2 wpre[2];                                  // first elements of the next LED's window, in flight across D
     if constexpr (Q_SMEM) {
-      const float2* wnext = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
-      int ir = tid / NC, jc = tid - ir * NC;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (tid + k * NT < NR * NC) wpre[k] = wnext[(p.ylo + ir) * L + p.xlo + jc];
-        ir += qNT; jc += rNT;
-        if (jc >= NC) { jc -= NC; ++ir; }
-      }
+      if (tid == 0) tma_store_window(Ocb[u & 1], &p.tmap, 2 * (c0 & ~1), r0, tile);   // updated window -> objFc
     }
+    // ===== D: the touched cells take their rebuilt maxima; max|objF|^2 = max over the whole grid =====
     for (int t = tid; t < ncr * ncc; t += NT) {          // one thread per touched cell
       const int a = t / ncc, b = t - a * ncc;
       float m = 0.f;
@@ -501,15 +574,6 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       m = warp_max(m);
       if (lane == 0) red[warp] = m;
     }
-    if constexpr (Q_SMEM) {                           // window of the next LED -> shared memory (C2 is done with Oc)
-      const float2* wnext = objFc + (size_t)(cr_next.y + H) * L + (cr_next.x + H);
-      int ir = tid / NC, jc = tid - ir * NC, k = 0;
-      for (int t = tid; t < NR * NC; t += NT, ++k) {
-        Oc[t] = (k == 0) ? wpre[0] : (k == 1) ? wpre[1] : wnext[(p.ylo + ir) * L + p.xlo + jc];
-        ir += qNT; jc += rNT;
-        if (jc >= NC) { jc -= NC; ++ir; }
-      }
-    }
     __syncthreads();
     FPM_TICK(9);
     {
@@ -518,6 +582,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
       for (int w = 1; w < NW; ++w) om2 = fmaxf(om2, red[w]);
       inv_objf_max = rsqrt_fast(om2);                // applied to P by the next S1 (or by the epilogue below)
     }
+    cr_a = cr_b; cr_b = cr_c;
     FPM_TICK(10);
   }
 
@@ -527,6 +592,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const UpdateParams
     for (int k = 0; k < 16; ++k) p.stage_clk[k] += tacc_[k];
   }
 #endif
+  if constexpr (Q_SMEM) { if (tid == 0) tma_store_wait_all(); }   // the last window stores have read their buffers
   // the last update's pupil increment is still pending
   for (int t = tid; t < NR * NC; t += NT) {
     const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;

@@ -1,6 +1,7 @@
 // fpmb200.cu -- C-ABI layer (include/fpmb200.h) over the sm_100a kernels of fpm_kernels.cuh.
 // Replaces the cv::UMat / cvComplex op sequence of runFPM() (fpmMain.cpp:274-498).
 // No CPU fallback: every entry point fails when no CUDA device can run the kernels.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -60,6 +61,9 @@ struct fpmb200_ctx {
   int max_smem_optin = 0, sm_count = 0;
   long long launches = 0;
   long long* stage_clk = nullptr;
+  CUtensorMap tmap;            // objFc as (2*L, L, n_tiles) floats with a (2*ocp, NR, 1) box
+  bool have_tmap = false;
+  int ocp = 0;
   char variant[160] = "unallocated";
 };
 
@@ -196,7 +200,10 @@ static size_t update_smem_bytes(const fpmb200_ctx* c, bool field_smem, bool p_sm
   if (field_smem) b += (sizeof(float2) * N * PITCH + 15) / 16 * 16;
   b += sizeof(float2) * N * 2 + sizeof(float) * 64;
   if (p_smem) b += bb;
-  if (q_smem) b += 2 * bb;                                                             // Qc + Oc
+  if (q_smem) {                                                                        // Qc + two TMA window buffers
+    const int NRb = c->yhi - c->ylo + 1, ocp = ((c->xhi - c->xlo + 1) + 2) & ~1;
+    b += bb + 128 + 2 * ((sizeof(float2) * (size_t)NRb * ocp + 127) / 128 * 128);
+  }
   b += sizeof(float) * (size_t)(c->L >> cs) * (c->L >> 4);                            // U
   if (q_smem) b += bb / 2;                                                             // Sc (support on the bbox)
   b += sizeof(unsigned) * (size_t)(((c->yhi - c->ylo + 1) >> cs) + 2) * (((c->xhi - c->xlo + 1) >> 4) + 2);   // Tm
@@ -232,7 +239,7 @@ extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
   // what lives in shared memory: prefer pupil + pupil-increment on chip with the finest max-cells that fit
   bool found = false;
   for (int pq = 0; pq < 3 && !found; ++pq) {
-    const bool ps = pq < 2, qs = pq < 1;
+    const bool ps = pq < 2, qs = pq < 1 && (2 * (((xhi - xlo + 1) + 2) & ~1) <= 256);   // TMA box <= 256 elements per dim
     for (int cs = 0; cs <= 4 && !found; ++cs) {
       if (sizeof(float) * (size_t)(c->L >> cs) * (c->L >> 4) > 48 * 1024) continue;
       if (update_smem_bytes(c, c->field_smem, ps, qs, cs) <= cap) {
@@ -249,6 +256,26 @@ extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
     CK(cudaMalloc(&c->qbuf, sizeof(float2) * (size_t)N * N * c->n_tiles));
     CK(cudaMemsetAsync(c->qbuf, 0, sizeof(float2) * (size_t)N * N * c->n_tiles, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+  }
+  c->ocp = ((xhi - xlo + 1) + 2) & ~1;       // even, with room for the 16-byte alignment of TMA box starts
+  c->have_tmap = false;
+  if (c->q_smem) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(FPMB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t gdim[3] = {(cuuint64_t)2 * c->L, (cuuint64_t)c->L, (cuuint64_t)c->n_tiles};
+    const cuuint64_t gstr[2] = {(cuuint64_t)2 * c->L * sizeof(float), (cuuint64_t)2 * c->L * c->L * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * c->ocp), (cuuint32_t)(yhi - ylo + 1), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((encode_fn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->objFc, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FPMB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    c->have_tmap = true;
   }
   snprintf(c->variant, sizeof c->variant,
            "fpm_update_kernel<N=%d,field=%s,pupil=%s,dP=%s> bbox=[%d..%d]x[%d..%d] maxcell=%dx16 smem=%zuB", N,
@@ -345,7 +372,7 @@ extern "C" int fpmb200_init_tiles(fpmb200_ctx* c, int first, int n, int init_slo
 
 template <int N, int NT, int MINB>
 static int launch_update(fpmb200_ctx* c, const UpdateParams& p, int n_blocks, cudaStream_t st) {
-  void (*k)(const UpdateParams) = nullptr;
+  void (*k)(const UpdateParams) = nullptr;   // (declared __grid_constant__ in the kernel)
   constexpr bool FS = (N <= 128);
   if (c->p_smem && c->q_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, true>;
   else if (c->p_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, false>;
@@ -365,7 +392,8 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
   p.tw = c->twN; p.field_gmem = c->field_gmem; p.qbuf = c->qbuf; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first;
   p.slot_begin = slot_begin; p.n_updates = n_updates;
   p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
-  p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi; p.cs = c->cs;
+  p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi; p.cs = c->cs; p.ocp = c->ocp;
+  if (c->have_tmap) p.tmap = c->tmap;
 #ifdef FPM_STAGE_TIMING
   if (!c->stage_clk) { CK(cudaMalloc(&c->stage_clk, 16 * sizeof(long long))); CK(cudaMemset(c->stage_clk, 0, 16 * sizeof(long long))); }
   p.stage_clk = c->stage_clk;

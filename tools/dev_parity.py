@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.joi
 import numpy as np
 import fpm_oracle as o
 import fpmb200
+if os.environ.get("FPM_LIB"): fpmb200.lib_path = lambda: os.path.join(fpmb200.LIB_DIR, os.environ["FPM_LIB"])
 import synth
 
 def setup(name, seed):
