@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include "fft_regs.cuh"
 #include "fpm_update.cuh"
+#include "fpm_update_cluster.cuh"
 
 namespace fpm {
 

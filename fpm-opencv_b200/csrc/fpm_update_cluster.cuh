@@ -1,0 +1,506 @@
+// fpm_update_cluster.cuh -- one tile's sub-aperture update spread over a thread-block cluster (sm_100a).
+//
+// Same arithmetic and stage structure as fpm_update.cuh (fpmMain.cpp:350-475 per update); here C CTAs of one
+// cluster share a tile, so a 256x256 field (512 KB) stays on chip and a single tile is no longer bound to one SM.
+//
+//   column passes (S1,S2,S6,S7), object / pupil update (C2): CTA k owns bbox columns [k*CPC, (k+1)*CPC) -- its
+//       slice of P, Q = pending pupil increment, the support and a column slab  cslab[column][row position]
+//   row passes (S3,S4,S5 incl. the amplitude replacement):   CTA k owns N/C scrambled row positions,
+//       row slab  rslab[row][column]
+//   The two transposes between them are written straight into the owner's shared memory (DSMEM stores issued by
+//   the producing butterfly, lanes contiguous in the destination) and fenced by barrier.cluster.
+//   max|objF| (fpmMain.cpp:460,467): the grid of cell maxima is distributed by cell row (cell row a lives in CTA
+//   a mod C); partial maxima of the touched cells are merged with DSMEM atomics, the slice maxima and max|P| are
+//   exchanged through per-rank slots.
+//   The spectrum window is read and written with plain coalesced loads/stores (each CTA touches only its own
+//   columns within an update; barrier.cluster orders them between updates).
+#pragma once
+#include <cooperative_groups.h>
+#include "fpm_update.cuh"
+
+namespace fpm {
+namespace cg = cooperative_groups;
+
+// Shared-memory carve-up, identical in every CTA of the cluster (DSMEM addresses are rank-mapped offsets).
+template <int N, int C> struct ClusterLayout {
+  size_t rslab, cslab, twA, twB, Pc, Qc, Sc, U, Tm, red, pmx, omx, total;
+  int gro, tmr, tmc;
+  __host__ __device__ ClusterLayout(int NR, int NC, int CPC, int L, int cs) {
+    using S = Shape<N>;
+    size_t o = 0;
+    rslab = o; o += (sizeof(float2) * (N / C) * S::PITCH + 15) / 16 * 16;
+    cslab = o; o += (sizeof(float2) * CPC * (N + 1) + 15) / 16 * 16;
+    twA = o; o += sizeof(float2) * N;
+    twB = o; o += sizeof(float2) * N;
+    Pc = o; o += (sizeof(float2) * NR * CPC + 15) / 16 * 16;
+    Qc = o; o += (sizeof(float2) * NR * CPC + 15) / 16 * 16;
+    Sc = o; o += (sizeof(float) * NR * CPC + 15) / 16 * 16;
+    gro = ((L >> cs) + C - 1) / C;                      // cell rows per CTA
+    U = o; o += (sizeof(float) * gro * (L >> 4) + 15) / 16 * 16;
+    tmr = (NR >> cs) + 2; tmc = (NC >> 4) + 2;
+    Tm = o; o += (sizeof(unsigned) * tmr * tmc + 15) / 16 * 16;
+    red = o; o += sizeof(float) * 64;
+    pmx = o; o += sizeof(float) * 16;
+    omx = o; o += sizeof(float) * 16;
+    total = o;
+  }
+};
+
+template <int N, int C, int NT>
+__global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_constant__ UpdateParams p) {
+  using S = Shape<N>;
+  constexpr int R1 = S::R1, R2 = S::R2, PITCH = S::PITCH, CH = S::CH;
+  constexpr int H = N / 2, NW = NT / 32;
+  constexpr int RPC = N / C;                // scrambled row positions per CTA
+  constexpr int PR = N + 1;                 // cslab pitch (float2 per column): odd, lanes = columns hit distinct banks
+  static_assert(RPC % R2 == 0 && RPC % 32 == 0, "a stage-B work item must not straddle two row owners");
+  static_assert(C <= 16, "per-rank slots");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = p.tile0 + blockIdx.x / C;
+  const int L = p.L;
+  const int NR = p.yhi - p.ylo + 1, NC = p.xhi - p.xlo + 1;
+  const int CPC = p.ocp;                                   // bbox columns per CTA (<= 32: one lane per column)
+  const int jc0 = rank * CPC;
+  const int ncl = max(0, min(CPC, NC - jc0));              // columns this CTA really has
+  const int gc = L >> 4, gr = L >> p.cs;
+
+  const ClusterLayout<N, C> lay(NR, NC, CPC, L, p.cs);
+  float2* rslab = reinterpret_cast<float2*>(smem_raw + lay.rslab);
+  float2* cslab = reinterpret_cast<float2*>(smem_raw + lay.cslab);
+  float2* twA = reinterpret_cast<float2*>(smem_raw + lay.twA);
+  float2* twB = reinterpret_cast<float2*>(smem_raw + lay.twB);
+  float2* Pc = reinterpret_cast<float2*>(smem_raw + lay.Pc);
+  float2* Qc = reinterpret_cast<float2*>(smem_raw + lay.Qc);
+  float* Sc = reinterpret_cast<float*>(smem_raw + lay.Sc);
+  float* U = reinterpret_cast<float*>(smem_raw + lay.U);          // cell rows a = rank, rank+C, ...: U[(a/C)*gc + b]
+  unsigned* Tm = reinterpret_cast<unsigned*>(smem_raw + lay.Tm);  // partial maxima of the touched cells (bit patterns)
+  float* red = reinterpret_cast<float*>(smem_raw + lay.red);
+  float* pmx = reinterpret_cast<float*>(smem_raw + lay.pmx);      // [C] max|P|^2 of every rank's slice
+  float* omx = reinterpret_cast<float*>(smem_raw + lay.omx);      // [C] max of every rank's share of U
+  float* W = reinterpret_cast<float*>(rslab);                     // |O_new|^2 on the slice; rslab is idle during C2/D
+  const int tmc = lay.tmc;
+
+  float2* objFc = p.objFc + (size_t)tile * L * L;
+  float2* Pg = p.pupil + (size_t)tile * N * N;
+  const float* __restrict__ stack = p.stack + (size_t)tile * p.n_leds * N * N;
+
+  // ---- prologue ----
+  for (int t = tid; t < N; t += NT) {
+    const int b = t / R2, a = t % R2;
+    twA[t] = p.tw[a * b];
+    const int a2 = t / R1, b2 = t % R1;
+    twB[t] = p.tw[a2 * b2];
+  }
+  for (int t = tid; t < NR * CPC; t += NT) {
+    const int ir = t / CPC, jcl = t - ir * CPC;
+    float2 pv = make_float2(0.f, 0.f);
+    float sv = 0.f;
+    if (jcl < ncl) {
+      const int iw = p.ylo + ir, jw = p.xlo + jc0 + jcl;
+      const int gi = (iw & (N - 1)) * N + (jw & (N - 1));
+      pv = Pg[gi]; sv = p.support[gi];
+    }
+    Pc[t] = pv; Sc[t] = sv; Qc[t] = make_float2(0.f, 0.f);
+  }
+  {
+    const int nown = (gr - rank + C - 1) / C;              // cell rows owned by this CTA
+    for (int it = warp; it < nown * (L >> 5); it += NW) {
+      const int la = it / (L >> 5), seg = it % (L >> 5);
+      const int cellrow = rank + la * C;
+      const float2* src = objFc + (size_t)(cellrow << p.cs) * L + (seg << 5) + lane;
+      float cm = 0.f;
+      for (int rr = 0; rr < (1 << p.cs); ++rr) {
+        const float2 o = __ldcg(src + (size_t)rr * L);
+        cm = fmaxf(cm, fmaf(o.x, o.x, o.y * o.y));
+      }
+      cm = half_warp_max(cm, lane);
+      if ((lane & 15) == 0) U[la * gc + 2 * seg + (lane >> 4)] = cm;
+    }
+  }
+  for (int t = tid; t < lay.tmr * lay.tmc; t += NT) Tm[t] = 0u;
+  cluster.sync();                                          // every CTA is resident and initialised before any remote write
+
+  const float kd1 = p.kappa * p.delta1, kd2 = p.kappa * p.delta2;
+  const float epsr = p.eps * (float)(N * N), epsi = p.kappa * epsr;   // the 1/N^2 of ifft2 is never applied (see fpm_update.cuh)
+  float inv_objf_max = 0.f;
+#ifdef FPM_STAGE_TIMING
+  long long tacc_[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tacc_[k] = 0;
+  long long tprev_ = clock64();
+#endif
+
+  for (int u = 0; u < p.n_updates; ++u) {
+    const int slot = (p.slot_begin + u) % p.n_leds;
+    const short2 cr = p.crop[slot];
+    const int xs = cr.x, ys = cr.y;
+    const float* __restrict__ img = stack + (size_t)slot * N * N;
+    const int r0 = ys + H + p.ylo, r1 = ys + H + p.yhi, c0 = xs + H + p.xlo, c1 = xs + H + p.xhi;   // rectangle (inclusive)
+    const int cr0 = r0 >> p.cs, ncr = (r1 >> p.cs) - cr0 + 1, cc0 = c0 >> 4, ncc = (c1 >> 4) - cc0 + 1;
+    const float2* wrow = objFc + (size_t)r0 * L + c0 + jc0;     // (ir, jcl) -> wrow[ir*L + jcl]
+#ifdef FPM_STAGE_TIMING
+    asm volatile("" ::"r"(xs));
+    FPM_TICK(11);
+#endif
+
+    if (tid < R1) {   // next LED's 1/I rows of this CTA towards L2: R1 chunks of RPC*R2 floats
+      const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
+      const float* nx = stack + (size_t)nslot * N * N + ((size_t)tid * N + rank * RPC) * R2;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)(RPC * R2 * 4)) : "memory");
+    }
+    // the cells this rectangle touches are rebuilt from scratch: their owners clear them now, the partial
+    // maxima arrive after the third cluster barrier of this update
+    for (int t = tid; t < ncr * ncc; t += NT) {
+      const int a = cr0 + t / ncc, b = cc0 + t % ncc;
+      if (a % C == rank) U[(a / C) * gc + b] = 0.f;
+    }
+
+    // ===== S1: pending pupil update (fpmMain.cpp:470-475), Phi = O*P, cols stage A (inverse) on this CTA's columns =====
+    {
+      float pm2 = 0.f;
+      for (int g = tid; g < R2 * 32; g += NT) {
+        const int i0 = g >> 5, jcl = g & 31;
+        if (jcl < ncl) {
+          float2 v[R1];
+#pragma unroll
+          for (int m = 0; m < R1; ++m) {               // all window loads first: one exposed latency, not R1
+            const int i = i0 + R2 * m;
+            const int iw = (i < H) ? i : i - N;
+            v[m] = (iw >= p.ylo && iw <= p.yhi) ? __ldcg(wrow + (size_t)(iw - p.ylo) * L + jcl) : make_float2(0.f, 0.f);
+          }
+#ifdef FPM_STAGE_TIMING
+#pragma unroll
+          for (int m = 0; m < R1; ++m) asm volatile("" ::"f"(v[m].x), "f"(v[m].y));
+          FPM_TICK(12);
+#endif
+#pragma unroll
+          for (int m = 0; m < R1; ++m) {
+            const int i = i0 + R2 * m;
+            const int iw = (i < H) ? i : i - N;
+            if (iw >= p.ylo && iw <= p.yhi) {
+              const int ir = iw - p.ylo;
+              const float2 O = v[m];
+              const float2 Q = Qc[ir * CPC + jcl];
+              float2 Pv = Pc[ir * CPC + jcl];
+              Pv.x = fmaf(Q.x, inv_objf_max, Pv.x);
+              Pv.y = fmaf(Q.y, inv_objf_max, Pv.y);
+              Pc[ir * CPC + jcl] = Pv;
+              pm2 = fmaxf(pm2, fmaf(Pv.x, Pv.x, Pv.y * Pv.y));
+              v[m] = cmul(O, Pv);
+            }
+          }
+          fftR<R1, true>(v);
+#pragma unroll
+          for (int k1 = 0; k1 < R1; ++k1) cslab[jcl * PR + i0 + R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
+        }
+      }
+#ifdef FPM_STAGE_TIMING
+      FPM_TICK(13);
+#endif
+      pm2 = warp_max(pm2);
+      if (lane == 0) red[32 + warp] = pm2;
+    }
+    __syncthreads();
+    FPM_TICK(1);
+    if (warp == 0) {                                        // this slice's max|P|^2 -> slot [rank] of every CTA
+      float m = (lane < NW) ? red[32 + lane] : 0.f;
+      m = warp_max(m);
+      if (lane < C) cluster.map_shared_rank(pmx, lane)[rank] = m;
+    }
+    // ===== S2: cols stage B (inverse); the results go to the owners of the row positions =====
+    for (int g = tid; g < R1 * 32; g += NT) {
+      const int k1 = g >> 5, jcl = g & 31;
+      if (jcl < ncl) {
+        const int js = (p.xlo + jc0 + jcl) & (N - 1);
+        float2 v[R2];
+#pragma unroll
+        for (int a = 0; a < R2; ++a) v[a] = cslab[jcl * PR + R2 * k1 + a];
+        fftR<R2, true>(v);
+        const int pos0 = R2 * k1;
+        float2* dst = cluster.map_shared_rank(rslab, pos0 / RPC) + (pos0 % RPC) * PITCH + js;
+#pragma unroll
+        for (int a = 0; a < R2; ++a) dst[a * PITCH] = v[a];
+      }
+    }
+#ifdef FPM_STAGE_TIMING
+    FPM_TICK(14);
+#endif
+    cluster.sync();                                         // #1: row slabs complete
+    FPM_TICK(2);
+    // 1/I of this CTA's S4 work items: issued now, consumed after S3
+    constexpr int S4R = (RPC * R1 + NT - 1) / NT;
+    constexpr bool S4PRE = (S4R * CH <= 8);
+    float4 ivall[S4PRE ? S4R : 1][CH];
+    if constexpr (S4PRE) {
+#pragma unroll
+      for (int rq = 0; rq < S4R; ++rq) {
+        const int g = tid + rq * NT;
+        if (g < RPC * R1) {
+          const int rl = g % RPC, k1 = g / RPC;
+          const float4* ip = reinterpret_cast<const float4*>(img) + ((size_t)k1 * N + rank * RPC + rl) * CH;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) ivall[rq][c] = __ldg(ip + c);
+        }
+      }
+    }
+    // ===== S3: rows stage A (inverse) on this CTA's rows; columns outside the bbox are zero, not read =====
+    for (int g = tid; g < RPC * R2; g += NT) {
+      const int rl = g % RPC, j0 = g / RPC;
+      float2* rp = rslab + rl * PITCH + j0;
+      float2 v[R1];
+#pragma unroll
+      for (int m = 0; m < R1; ++m) {
+        const int col = j0 + R2 * m;
+        const int jw = (R2 * m < H) ? col : col - N;
+        v[m] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);
+      }
+      fftR<R1, true>(v);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
+    }
+    __syncthreads();
+    FPM_TICK(3);
+    // ===== S4: rows stage B (inverse) + amplitude replacement (fpmMain.cpp:378-393) + rows stage B' (forward) =====
+#pragma unroll
+    for (int rq = 0; rq < S4R; ++rq) {
+      const int g = tid + rq * NT;
+      if (g >= RPC * R1) break;
+      const int rl = g % RPC, k1 = g / RPC;
+      float4 iv[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        if constexpr (S4PRE) iv[c] = ivall[rq][c];
+        else iv[c] = __ldg(reinterpret_cast<const float4*>(img) + ((size_t)k1 * N + rank * RPC + rl) * CH + c);
+      }
+      float2* rp = rslab + rl * PITCH + R2 * k1;
+      float2 v[R2];
+#pragma unroll
+      for (int a = 0; a < R2; ++a) v[a] = rp[a];
+      fftR<R2, true>(v);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) {
+        const float4 q4 = iv[k2 >> 2];
+        const int e = k2 & 3;
+        const float inv_i = (e == 0) ? q4.x : (e == 1) ? q4.y : (e == 2) ? q4.z : q4.w;
+        const float2 tt = cadd(v[k2], make_float2(epsr, epsi));
+        const float sc = rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y) * inv_i);
+        v[k2] = cscale(v[k2], sc);
+      }
+      fftR<R2, false>(v);
+#pragma unroll
+      for (int q = 0; q < R2; ++q) rp[q] = twmul<false>(v[q], twB[q * R1 + k1]);
+    }
+    __syncthreads();
+    FPM_TICK(4);
+    // ===== S5: rows stage A' (forward); bbox columns go to the column owners =====
+    for (int g = tid; g < RPC * R2; g += NT) {
+      const int rl = g % RPC, q = g / RPC;
+      const float2* rp = rslab + rl * PITCH + q;
+      float2 v[R1];
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) v[k1] = rp[R2 * k1];
+      fftR<R1, false>(v);
+      const int pos = rank * RPC + rl;
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        const int col = R2 * r + q;
+        const int jw = (R2 * r < H) ? col : col - N;
+        if (jw >= p.xlo && jw <= p.xhi) {
+          const int jc = jw - p.xlo;
+          const int dk = jc / CPC;
+          cluster.map_shared_rank(cslab, dk)[(jc - dk * CPC) * PR + pos] = v[r];
+        }
+      }
+    }
+#ifdef FPM_STAGE_TIMING
+    FPM_TICK(15);
+#endif
+    cluster.sync();                                         // #2: column slabs complete
+    FPM_TICK(5);
+    float pm2c = pmx[0];                                    // max|P|^2 over the whole pupil (all ranks' slices)
+#pragma unroll
+    for (int k = 1; k < C; ++k) pm2c = fmaxf(pm2c, pmx[k]);
+    // ===== S6: cols stage B' (forward) =====
+    for (int g = tid; g < R1 * 32; g += NT) {
+      const int k1 = g >> 5, jcl = g & 31;
+      if (jcl < ncl) {
+        float2* cp = cslab + jcl * PR + R2 * k1;
+        float2 v[R2];
+#pragma unroll
+        for (int a = 0; a < R2; ++a) v[a] = cp[a];
+        fftR<R2, false>(v);
+#pragma unroll
+        for (int q = 0; q < R2; ++q) cp[q] = twmul<false>(v[q], twB[q * R1 + k1]);
+      }
+    }
+    __syncthreads();
+    FPM_TICK(6);
+    // ===== S7: cols stage A' (forward) -> Phi' in natural row order; only bbox rows are stored =====
+    for (int g = tid; g < R2 * 32; g += NT) {
+      const int q = g >> 5, jcl = g & 31;
+      if (jcl < ncl) {
+        float2* cp = cslab + jcl * PR;
+        float2 v[R1];
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) v[k1] = cp[R2 * k1 + q];
+        fftR<R1, false>(v);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          const int i = R2 * r + q;
+          const int iw = (i < H) ? i : i - N;
+          if (iw >= p.ylo && iw <= p.yhi) cp[i] = v[r];
+        }
+      }
+    }
+    __syncthreads();
+    FPM_TICK(7);
+    // ===== C2: object update (fpmMain.cpp:406-447) and pupil-increment numerator (:459-472) on this CTA's columns =====
+    {
+      const float inv_pmax = rsqrt_fast(pm2c);
+      float2* wr = objFc + (size_t)r0 * L + c0 + jc0;
+      constexpr int UN = (N == 256) ? 12 : 6;               // every window row of a warp in flight at once
+      for (int base = warp; base < NR; base += UN * NW) {
+        float2 Ov[UN];
+#pragma unroll
+        for (int k = 0; k < UN; ++k) {
+          const int ir = base + k * NW;
+          Ov[k] = (ir < NR && lane < ncl) ? __ldcg(wr + (size_t)ir * L + lane) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < UN; ++k) {
+          const int ir = base + k * NW;
+          if (ir < NR && lane < CPC) {
+            float a2n = 0.f;
+            if (lane < ncl) {
+              const int iw = p.ylo + ir, i = iw & (N - 1);
+              const int e = ir * CPC + lane;
+              const float2 O = Ov[k];
+              const float2 Pv = Pc[e];
+              const float2 d = csub(cslab[lane * PR + i], cmul(O, Pv));           // dPhi = Phi' - Phi
+              const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
+              const float2 num = cmulc(d, Pv);
+              const float A = pa2 + p.delta2;
+              const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
+              const float2 On = make_float2(O.x + (num.x * A + num.y * kd2) * sc, O.y + (num.y * A - num.x * kd2) * sc);
+              wr[(size_t)ir * L + lane] = On;
+              a2n = fmaf(On.x, On.x, On.y * On.y);
+              const float oa2 = fmaf(O.x, O.x, O.y * O.y);
+              const float2 numq = cmulc(d, O);
+              const float A1 = oa2 + p.delta1;
+              const float sq = __fdividef(sqrt_fast(oa2) * Sc[e], fmaf(A1, A1, kd1 * kd1));
+              Qc[e] = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
+            }
+            W[ir * CPC + lane] = a2n;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    FPM_TICK(8);
+    // ===== D: exact max|objF|.  Partial maxima of the touched cells: this slice's new values (from W) ... =====
+    if (ncl > 0) {
+      const int ca0 = c0 + jc0, ca1 = ca0 + ncl - 1;                    // absolute columns of the slice
+      const int lcc0 = ca0 >> 4, nlc = (ca1 >> 4) - lcc0 + 1;
+      for (int t = tid; t < NR * nlc; t += NT) {
+        const int ir = t / nlc, bl = t - ir * nlc;
+        const int lo = max(ca0, (lcc0 + bl) << 4), hi = min(ca1, ((lcc0 + bl) << 4) + 15);
+        const float* wp = W + ir * CPC - ca0;
+        float m = 0.f;
+        for (int c = lo; c <= hi; ++c) m = fmaxf(m, wp[c]);
+        atomicMax(&Tm[(((r0 + ir) >> p.cs) - cr0) * tmc + (lcc0 + bl - cc0)], __float_as_uint(m));
+      }
+    }
+    // ... and the pixels of those cells outside the rectangle, which this update does not change (shared out over the
+    // cluster): strips above / below (full width of the touched cells) and left / right (rectangle rows)
+    {
+      const int wc0 = cc0 << 4, wcols = ncc << 4, rt0 = cr0 << p.cs, rt1 = ((cr0 + ncr) << p.cs) - 1;
+      const int n_top = (r0 - rt0) * wcols, n_bot = (rt1 - r1) * wcols;
+      const int wl = c0 - wc0, wrt = wc0 + wcols - 1 - c1;
+      const int n_left = NR * wl, n_right = NR * wrt;
+      const int n_all = n_top + n_bot + n_left + n_right;
+      constexpr int DU = 4;
+      for (int base = rank * NT + tid; base < n_all; base += DU * C * NT) {
+        float2 o[DU];
+        int cell[DU];
+#pragma unroll
+        for (int k = 0; k < DU; ++k) {
+          const int t = base + k * C * NT;
+          cell[k] = -1;
+          if (t < n_all) {
+            int r, c;
+            if (t < n_top) { r = rt0 + t / wcols; c = wc0 + t % wcols; }
+            else if (t < n_top + n_bot) { const int s = t - n_top; r = r1 + 1 + s / wcols; c = wc0 + s % wcols; }
+            else if (t < n_top + n_bot + n_left) { const int s = t - n_top - n_bot; r = r0 + s / wl; c = wc0 + s % wl; }
+            else { const int s = t - n_top - n_bot - n_left; r = r0 + s / wrt; c = c1 + 1 + s % wrt; }
+            o[k] = __ldcg(objFc + (size_t)r * L + c);
+            cell[k] = ((r >> p.cs) - cr0) * tmc + ((c >> 4) - cc0);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DU; ++k)
+          if (cell[k] >= 0) atomicMax(&Tm[cell[k]], __float_as_uint(fmaf(o[k].x, o[k].x, o[k].y * o[k].y)));
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < ncr * ncc; t += NT) {              // merge into the owners' grids
+      const int ta = t / ncc, tb = t - ta * ncc;
+      const unsigned v = Tm[ta * tmc + tb];
+      Tm[ta * tmc + tb] = 0u;
+      if (v) {
+        const int a = cr0 + ta;
+        atomicMax(reinterpret_cast<unsigned*>(cluster.map_shared_rank(U, a % C)) + (a / C) * gc + cc0 + tb, v);
+      }
+    }
+    cluster.sync();                                         // #3: grids complete; this update's spectrum stores are ordered
+    FPM_TICK(9);
+    {
+      const int nown = (gr - rank + C - 1) / C;
+      const float4* U4 = reinterpret_cast<const float4*>(U);
+      const int n4 = (nown * gc) >> 2;
+      float m = 0.f;
+      for (int t = tid; t < n4; t += NT) { const float4 q = U4[t]; m = fmaxf(fmaxf(m, fmaxf(q.x, q.y)), fmaxf(q.z, q.w)); }
+      m = warp_max(m);
+      if (lane == 0) red[warp] = m;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float m = (lane < NW) ? red[lane] : 0.f;
+      m = warp_max(m);
+      if (lane < C) cluster.map_shared_rank(omx, lane)[rank] = m;
+    }
+    cluster.sync();                                         // #4
+    {
+      float om2 = omx[0];
+#pragma unroll
+      for (int k = 1; k < C; ++k) om2 = fmaxf(om2, omx[k]);
+      inv_objf_max = rsqrt_fast(om2);
+    }
+    FPM_TICK(10);
+  }
+
+#ifdef FPM_STAGE_TIMING
+  if (tid == 0 && blockIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) p.stage_clk[k] += tacc_[k];
+  }
+#endif
+  // the last update's pupil increment is still pending
+  for (int t = tid; t < NR * CPC; t += NT) {
+    const int ir = t / CPC, jcl = t - ir * CPC;
+    if (jcl < ncl) {
+      const float2 Q = Qc[t];
+      float2 v = Pc[t];
+      v.x = fmaf(Q.x, inv_objf_max, v.x);
+      v.y = fmaf(Q.y, inv_objf_max, v.y);
+      const int iw = p.ylo + ir, jw = p.xlo + jc0 + jcl;
+      Pg[(iw & (N - 1)) * N + (jw & (N - 1))] = v;
+    }
+  }
+  cluster.sync();                                           // no CTA exits while its shared memory may still be addressed
+}
+
+}  // namespace fpm

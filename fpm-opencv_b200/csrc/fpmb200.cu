@@ -64,8 +64,13 @@ struct fpmb200_ctx {
   CUtensorMap tmap;            // objFc as (2*L, L, n_tiles) floats with a (2*ocp, NR, 1) box
   bool have_tmap = false;
   int ocp = 0;
-  char variant[160] = "unallocated";
+  int cluster_req = 0;         // CTAs per tile asked for (0 = choose)
+  int cluster = 1;             // CTAs per tile in use (1 = fpm_update_kernel, >1 = fpm_update_cluster_kernel)
+  int cpc = 0;                 // bbox columns per CTA of the cluster kernel
+  char variant[200] = "unallocated";
 };
+
+static int select_variant(fpmb200_ctx* c);
 
 extern "C" const char* fpmb200_last_error(void) { return g_err.c_str(); }
 extern "C" int fpmb200_abi_version(void) { return 1; }
@@ -177,6 +182,13 @@ extern "C" int fpmb200_set_params(fpmb200_ctx* c, float delta1, float delta2, fl
   return FPMB200_OK;
 }
 
+extern "C" int fpmb200_set_cluster(fpmb200_ctx* c, int ctas_per_tile) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  if (ctas_per_tile < 0 || ctas_per_tile > 8) return fail(FPMB200_ERR_ARG, "ctas_per_tile must be 0 (choose), 1, 2, 4 or 8");
+  c->cluster_req = ctas_per_tile;
+  return c->have_support ? select_variant(c) : FPMB200_OK;
+}
+
 extern "C" int fpmb200_upload_leds(fpmb200_ctx* c, const int16_t* cx, const int16_t* cy, int n_leds) {
   if (!c || !cx || !cy) return fail(FPMB200_ERR_ARG, "NULL argument");
   if (!c->n_tiles) return fail(FPMB200_ERR_STATE, "fpmb200_tiles_alloc first");
@@ -233,7 +245,63 @@ extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
   CK(cudaSetDevice(c->device));
   CK(copy_sync(c, c->support, mask, sizeof(float) * N * N, cudaMemcpyHostToDevice));
   c->have_support = true;
-  // ---- choose the kernel variant for this (N, L, bbox): what lives in shared memory ----
+  return select_variant(c);
+}
+
+template <int N, int C>
+static bool cluster_fits(fpmb200_ctx* c, int* cpc_out, int* cs_out, size_t* bytes_out) {
+  const int NR = c->yhi - c->ylo + 1, NC = c->xhi - c->xlo + 1;
+  const int cpc = (NC + C - 1) / C;
+  if (cpc > 32) return false;                                  // one lane per column in the column passes
+  for (int cs = 0; cs <= 4; ++cs) {
+    const ClusterLayout<N, C> lay(NR, NC, cpc, c->L, cs);
+    if (sizeof(float) * (size_t)lay.gro * (c->L >> 4) > 8 * 1024) continue;      // scanned once per update
+    if (sizeof(float) * (size_t)NR * cpc > sizeof(float2) * (size_t)(N / C) * (N + 1)) continue;   // W aliases the row slab
+    if (lay.total > (size_t)c->max_smem_optin) continue;
+    auto k = fpm_update_cluster_kernel<N, C, 512>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(C, 1, 1); cfg.blockDim = dim3(512, 1, 1); cfg.dynamicSmemBytes = lay.total;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, k, &cfg) != cudaSuccess || n_clusters < 1) { cudaGetLastError(); continue; }
+    *cpc_out = cpc; *cs_out = cs; *bytes_out = lay.total;
+    return true;
+  }
+  return false;
+}
+
+// ---- choose the kernel variant for this (N, L, bbox): CTAs per tile and what lives in shared memory ----
+static int select_variant(fpmb200_ctx* c) {
+  const int N = c->N;
+  const int ylo = c->ylo, yhi = c->yhi, xlo = c->xlo, xhi = c->xhi;
+  CK(cudaSetDevice(c->device));
+  // A 256x256 field does not fit one SM: spread the tile over a cluster of 8 CTAs (field, pupil and pupil increment on
+  // chip, transposes through DSMEM).  128x128 tiles use a cluster only on request (fpmb200_set_cluster).
+  c->cluster = 1;
+  {
+    // default: 256x256 tiles always (the field does not fit one SM otherwise); 128x128 tiles when there are so few
+    // tiles that a quarter of the SMs would idle anyway (single-tile runs: lower latency per update)
+    const int want = c->cluster_req ? c->cluster_req : (N == 256 ? 8 : (N == 128 && c->n_tiles * 4 <= c->sm_count) ? 4 : 1);
+    bool ok = false;
+    if (N == 256 && want == 8) ok = cluster_fits<256, 8>(c, &c->cpc, &c->cs, &c->smem_bytes);
+    else if (N == 128 && want == 4) ok = cluster_fits<128, 4>(c, &c->cpc, &c->cs, &c->smem_bytes);
+    else if (N == 128 && want == 2) ok = cluster_fits<128, 2>(c, &c->cpc, &c->cs, &c->smem_bytes);
+    else if (want != 1 && c->cluster_req)
+      return fail(FPMB200_ERR_ARG, "%d CTAs per tile is not available for Np=%d (256: 8; 128: 2 or 4; any: 1)", want, N);
+    if (ok) {
+      c->cluster = want;
+      snprintf(c->variant, sizeof c->variant,
+               "fpm_update_cluster_kernel<N=%d,cluster=%d> bbox=[%d..%d]x[%d..%d] cols/CTA=%d maxcell=%dx16 smem=%zuB", N, want,
+               ylo, yhi, xlo, xhi, c->cpc, 1 << c->cs, c->smem_bytes);
+      return FPMB200_OK;
+    }
+    if (c->cluster_req > 1) return fail(FPMB200_ERR_ARG, "the %d-CTA cluster kernel does not fit this geometry (Np=%d, Nlarge=%d)", want, N, c->L);
+  }
   const size_t cap = (size_t)c->max_smem_optin;
   c->field_smem = (N <= 128);
   // what lives in shared memory: prefer pupil + pupil-increment on chip with the finest max-cells that fit
@@ -384,6 +452,21 @@ static int launch_update(fpmb200_ctx* c, const UpdateParams& p, int n_blocks, cu
   return FPMB200_OK;
 }
 
+template <int N, int C>
+static int launch_cluster(fpmb200_ctx* c, const UpdateParams& p, int n_tiles, cudaStream_t st) {
+  auto k = fpm_update_cluster_kernel<N, C, 512>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(n_tiles * C, 1, 1); cfg.blockDim = dim3(512, 1, 1); cfg.dynamicSmemBytes = c->smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, k, p));
+  c->launches++;
+  return FPMB200_OK;
+}
+
 static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
   if (!c->have_support || !c->have_leds) return fail(FPMB200_ERR_STATE, "upload LED tables and the pupil support first");
   UpdateParams p;
@@ -399,6 +482,13 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
   p.stage_clk = c->stage_clk;
 #endif
   CK(cudaSetDevice(c->device));
+  if (c->cluster > 1) {
+    p.ocp = c->cpc;
+    if (c->N == 256 && c->cluster == 8) return launch_cluster<256, 8>(c, p, n, st);
+    if (c->N == 128 && c->cluster == 4) return launch_cluster<128, 4>(c, p, n, st);
+    if (c->N == 128 && c->cluster == 2) return launch_cluster<128, 2>(c, p, n, st);
+    return fail(FPMB200_ERR_STATE, "no cluster kernel for Np=%d x %d CTAs", c->N, c->cluster);
+  }
   switch (c->N) {
     case 64: return launch_update<64, 256, 2>(c, p, n, st);
     case 128: return launch_update<128, 512, 1>(c, p, n, st);

@@ -40,6 +40,7 @@ def load():
         "fpmb200_destroy": (None, [vp]),
         "fpmb200_tiles_alloc": (i, [vp, i, i, i, i]),
         "fpmb200_set_params": (i, [vp, f, f, f, i]),
+        "fpmb200_set_cluster": (i, [vp, i]),
         "fpmb200_upload_leds": (i, [vp, vp, vp, i]),
         "fpmb200_upload_pupil_support": (i, [vp, vp]),
         "fpmb200_upload_stack": (i, [vp, i, i, vp, vp]),
@@ -63,7 +64,7 @@ def load():
 
 
 EXPORTS = ["fpmb200_last_error", "fpmb200_abi_version", "fpmb200_create", "fpmb200_destroy",
-           "fpmb200_tiles_alloc", "fpmb200_set_params", "fpmb200_upload_leds",
+           "fpmb200_tiles_alloc", "fpmb200_set_params", "fpmb200_set_cluster", "fpmb200_upload_leds",
            "fpmb200_upload_pupil_support", "fpmb200_upload_stack", "fpmb200_init_tiles", "fpmb200_run",
            "fpmb200_step", "fpmb200_finalize", "fpmb200_upload_state", "fpmb200_download",
            "fpmb200_download_objcrop", "fpmb200_device_buffer", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
@@ -109,6 +110,9 @@ class Context:
 
     def set_params(self, delta1, delta2, eps, literal_scalar=1):
         self._ck(self.L.fpmb200_set_params(self._h, float(delta1), float(delta2), float(eps), int(literal_scalar)))
+
+    def set_cluster(self, ctas_per_tile):
+        self._ck(self.L.fpmb200_set_cluster(self._h, int(ctas_per_tile)))
 
     def upload_leds(self, cropX, cropY):
         cx = np.ascontiguousarray(cropX, dtype=np.int16)

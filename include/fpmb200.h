@@ -57,6 +57,12 @@ int fpmb200_tiles_alloc(fpmb200_ctx* ctx, int n_tiles, int Np, int Nlarge, int n
  * shipped source does against stock OpenCV: complex denominators), 0 = real part only. */
 int fpmb200_set_params(fpmb200_ctx* ctx, float delta1, float delta2, float eps, int literal_scalar);
 
+/* CTAs per tile of the update kernel: 0 = let the library choose (default: a cluster of 8 CTAs with the field in
+ * distributed shared memory for Np=256, one CTA per tile otherwise), 1 = one CTA per tile, 2 / 4 (Np=128) or
+ * 8 (Np=256) = a thread-block cluster per tile (lower single-tile latency; fewer tiles in flight).  The
+ * reference has no counterpart: it is the choice its OpenCL queue makes implicitly (fpmMain.cpp:345-476). */
+int fpmb200_set_cluster(fpmb200_ctx* ctx, int ctas_per_tile);
+
 /* Per-slot crop origins (fpmMain.cpp:157-165), already in update order.  Each must satisfy
  * 0 <= start <= Nlarge-Np. */
 int fpmb200_upload_leds(fpmb200_ctx* ctx, const int16_t* cropXStart, const int16_t* cropYStart, int n_leds);

@@ -47,12 +47,14 @@ class Case:
         c = self.cfg
         return orc.run(self.stack, self.cx, self.cy, self.L, self.r, c.delta1, c.delta2, c.eps, iters, kappa, trace=trace)
 
-    def make_ctx(self, n_tiles=1, kappa=1, support=None, device=0):
+    def make_ctx(self, n_tiles=1, kappa=1, support=None, device=0, cluster=None):
         import fpmb200
         c = self.cfg
         ctx = fpmb200.Context(device)
         ctx.tiles_alloc(n_tiles, self.N, self.L, len(self.cx))
         ctx.set_params(c.delta1, c.delta2, c.eps, kappa)
+        if cluster is not None:
+            ctx.set_cluster(cluster)
         ctx.upload_leds(self.cx, self.cy)
         ctx.upload_pupil_support(self.support if support is None else support)
         for t in range(n_tiles):

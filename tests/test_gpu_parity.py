@@ -65,9 +65,14 @@ def test_init_state(name):
 @pytest.mark.parametrize("name,n_steps", [("cfg1_mono_np64", 117), ("cfg2_fLEDc_np128", 89), ("cfg3b_cellScope_np64", 60),
                                           ("cfg5_cellscope2_np128", 40)])
 @pytest.mark.parametrize("kappa", [1, 0])
-def test_per_step_parity(name, n_steps, kappa):
+@pytest.mark.parametrize("ctas", [1, 0])
+def test_per_step_parity(name, n_steps, kappa, ctas):
+    """ctas = CTAs per tile: 1 = fpm_update_kernel, 0 = the library's choice (a 4-CTA cluster for one 128x128 tile)."""
     c = T.case(name)
-    ctx = c.make_ctx(kappa=kappa)
+    if ctas == 0 and c.N != 128:
+        pytest.skip("same kernel as ctas=1")
+    ctx = c.make_ctx(kappa=kappa, cluster=ctas)
+    assert ("cluster_kernel" in ctx.variant) == (ctas == 0)
     st = orc.init_state(c.stack, c.L, c.r)
     # warm the oracle state up so that the pupil is not the trivial binary mask
     for k in range(len(c.cx)):
@@ -86,9 +91,13 @@ def test_per_step_parity(name, n_steps, kappa):
 @pytest.mark.parametrize("name,iters", [("cfg1_mono_np64", 10), ("cfg2_fLEDc_np128", 10), ("cfg3b_cellScope_np64", 3),
                                         ("cfg4_dogStomach_np128", 10), ("cfg5_cellscope2_np128", 4),
                                         ("cfg6_mono_dome_np64", 3)])
-def test_full_run_parity(name, iters):
+@pytest.mark.parametrize("ctas", [1, 0])
+def test_full_run_parity(name, iters, ctas):
     c = T.case(name)
-    ctx = c.make_ctx()
+    if ctas == 0 and c.N != 128:
+        pytest.skip("same kernel as ctas=1")
+    ctx = c.make_ctx(cluster=ctas)
+    assert ("cluster_kernel" in ctx.variant) == (ctas == 0)
     ctx.run(iters)
     ctx.finalize()
     st = c.oracle_run(iters)
@@ -107,10 +116,13 @@ def test_full_run_parity_kappa0():
 
 
 @pytest.mark.parametrize("name,n_leds,iters", [("cfg5b_cellscope2_np256", 40, 2), ("cfg3_cellScope_np256", 24, 1)])
-def test_np256_tiles(name, n_leds, iters):
-    """Np=256 (field does not fit one SM's shared memory; Nlarge 1024 / 1536 = 3*2^9)."""
+@pytest.mark.parametrize("ctas", [8, 1])
+def test_np256_tiles(name, n_leds, iters, ctas):
+    """Np=256, Nlarge 1024 / 1536 = 3*2^9.  The field does not fit one SM's shared memory: 8 CTAs of a cluster share
+    the tile (default); with one CTA per tile the field lives in a global scratch buffer."""
     c = T.case(name, n_leds=n_leds)
-    ctx = c.make_ctx()
+    ctx = c.make_ctx(cluster=ctas)
+    assert ("cluster=8" in ctx.variant) == (ctas == 8)
     ctx.run(iters)
     ctx.finalize()
     e = compare(ctx, c.oracle_run(iters))
@@ -180,6 +192,35 @@ def test_windows_touching_the_spectrum_border():
     ctx.finalize()
     compare(ctx, c.oracle_run(2))
     ctx.close()
+
+
+@pytest.mark.parametrize("name,ctas,n_leds", [("cfg2_fLEDc_np128", 2, 20), ("cfg2_fLEDc_np128", 4, 20), ("cfg5_cellscope2_np128", 4, 12),
+                                              ("cfg5b_cellscope2_np256", 8, 10)])
+def test_cluster_kernel(name, ctas, n_leds):
+    """The cluster kernel on several tiles at once (more clusters than fit: they run in waves), windows at the
+    spectrum border, and n single-update launches == one persistent launch bit for bit (the DSMEM max merges are
+    order-independent)."""
+    c = T.Case(name, 8, n_leds)
+    c.cx = c.cx.copy(); c.cy = c.cy.copy()
+    c.cx[2], c.cy[2] = 0, 0
+    c.cx[3], c.cy[3] = c.L - c.N, c.L - c.N
+    c.cx[4], c.cy[4] = 1, c.L - c.N - 1
+    c.stack = None
+    import synth
+    c.stack = synth.synth_stack(c.N, c.L, c.r, c.cx, c.cy, 8)
+    n_tiles = 40 if c.N == 128 else 3
+    a, b = c.make_ctx(n_tiles=n_tiles, cluster=ctas), c.make_ctx(cluster=ctas)
+    assert "cluster=%d" % ctas in a.variant
+    a.run(1)
+    for k in range(n_leds):
+        b.step(0, k)
+    a.finalize(); b.finalize()
+    ref = b.download(0)
+    for t in (0, n_tiles - 1):
+        for x, y in zip(a.download(t), ref):
+            assert np.array_equal(x, y)
+    compare(a, c.oracle_run(1), tile=n_tiles - 1)
+    a.close(), b.close()
 
 
 def test_steps_equal_run_bitwise():

@@ -25,6 +25,7 @@ def main():
         ctx = fpmb200.Context(0)
         ctx.tiles_alloc(1, N, L, n)
         ctx.set_params(cfg.delta1, cfg.delta2, cfg.eps, 1)
+        if os.environ.get("FPM_CLUSTER"): ctx.set_cluster(int(os.environ["FPM_CLUSTER"]))
         ctx.upload_leds(cx, cy)
         ctx.upload_pupil_support(o.pupil_support(N, cfg.naRadius))
         print(name, ctx.variant, flush=True)
@@ -36,7 +37,7 @@ def main():
         print(" init objF", o.rel_l2(gF, np.fft.ifftshift(ost.objFc)), "P", o.rel_l2(gP, ost.P), flush=True)
         # per-step from the oracle's state
         worst = 0
-        for k in range(min(n, 40)):
+        for k in range(min(n, int(os.environ.get("FPM_STEPS", "40")))):
             ctx.upload_state(0, np.fft.ifftshift(ost.objFc), ost.P)
             o.update(ost, st[k], cx[k], cy[k], cfg.delta1, cfg.delta2, cfg.eps, 1)
             ctx.step(0, k)
@@ -46,7 +47,7 @@ def main():
             if k < 3 or not np.isfinite(eF): print("  step", k, eF, eP, flush=True)
         print(" per-step worst rel-L2", worst, flush=True)
         # full run
-        iters = 10
+        iters = int(os.environ.get("FPM_ITERS", "10"))
         ctx.init_tiles(); ctx.sync()
         t = time.perf_counter(); ctx.run(iters); ctx.sync(); dt = time.perf_counter() - t
         ctx.finalize(); ctx.sync()

@@ -9,8 +9,8 @@ import fpm_testlib as T
 names = sys.argv[1:] or ["cfg2_fLEDc_np128"]
 for name in names:
     c = T.Case(name, 1)
-    for n_tiles in (1, 148):
-        ctx = c.make_ctx(n_tiles=n_tiles)
+    for n_tiles in [int(x) for x in os.environ.get("FPM_TILES", "1,148").split(",")]:
+        ctx = c.make_ctx(n_tiles=n_tiles, cluster=int(os.environ["FPM_CLUSTER"]) if os.environ.get("FPM_CLUSTER") else None)
         ctx.run(1); ctx.sync()
         buf = (C.c_longlong * 16)()
         ctx.L.fpmb200_stage_clocks.argtypes = [C.c_void_p, C.c_void_p]
@@ -22,7 +22,7 @@ for name in names:
         labels = ["-", "S1 colA(inv)+O*P", "S2 colB(inv)", "S3 rowA(inv)", "S4 rowB+amp+rowB'", "S5 rowA'", "S6 colB'", "S7 colA'", "C2 object update", "D max|objF|", "E pupil+next window"]
         print(name, "tiles", n_tiles, ctx.variant)
         for k in range(1, 11):
-            print("   %-20s %8.0f cyc  %5.1f%%" % (labels[k], v[k], 100 * v[k] / v[1:11].sum()))
-        print("   total %.0f cycles/update" % v[1:11].sum())
+            print("   %-20s %8.0f cyc  %5.1f%%" % (labels[k], v[k], 100 * v[k] / v[1:16].sum()))
+        print("   total %.0f cycles/update" % v[1:11].sum(), " extra ticks 11..15:", " ".join("%.0f" % x for x in v[11:16]))
         pass
         ctx.close()
