@@ -21,9 +21,38 @@
 namespace fpm {
 namespace cg = cooperative_groups;
 
+// ---- DSMEM primitives: remote stores that signal the destination CTA's mbarrier (no cluster-wide fence) ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, int rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f2(uint32_t raddr, float2 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(raddr), "f"(v.x), "f"(v.y), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+               ::"r"(raddr), "f"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// relaxed: the caller issues ONE fence.acq_rel.cluster before a batch of these (a .release arrive costs a
+// MEMBAR.ALL.GPU each)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+
 // Shared-memory carve-up, identical in every CTA of the cluster (DSMEM addresses are rank-mapped offsets).
 template <int N, int C> struct ClusterLayout {
-  size_t rslab, cslab, twA, twB, Pc, Qc, Sc, U, Tm, red, pmx, omx, total;
+  size_t rslab, cslab, twA, twB, Pc, Qc, Sc, U, Tm, red, pmx, omx, bars, total;
   int gro, tmr, tmc;
   __host__ __device__ ClusterLayout(int NR, int NC, int CPC, int L, int cs) {
     using S = Shape<N>;
@@ -42,6 +71,7 @@ template <int N, int C> struct ClusterLayout {
     red = o; o += sizeof(float) * 64;
     pmx = o; o += sizeof(float) * 16;
     omx = o; o += sizeof(float) * 16;
+    bars = o; o += sizeof(uint64_t) * 4;
     total = o;
   }
 };
@@ -64,6 +94,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   const int L = p.L;
   const int NR = p.yhi - p.ylo + 1, NC = p.xhi - p.xlo + 1;
   const int CPC = p.ocp;                                   // bbox columns per CTA (<= 32: one lane per column)
+  const int cpc_inv = (65536 + CPC - 1) / CPC;
   const int jc0 = rank * CPC;
   const int ncl = max(0, min(CPC, NC - jc0));              // columns this CTA really has
   const int gc = L >> 4, gr = L >> p.cs;
@@ -81,6 +112,11 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   float* red = reinterpret_cast<float*>(smem_raw + lay.red);
   float* pmx = reinterpret_cast<float*>(smem_raw + lay.pmx);      // [C] max|P|^2 of every rank's slice
   float* omx = reinterpret_cast<float*>(smem_raw + lay.omx);      // [C] max of every rank's share of U
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + lay.bars);
+  uint64_t* rbar = bars + 0;   // row slab (+ max|P|^2 slots) complete: counts the bytes of the remote st.async
+  uint64_t* cbar = bars + 1;   // column slab complete
+  uint64_t* ubar = bars + 2;   // every rank has merged its cell maxima (C arrivals); also orders the spectrum stores
+  uint64_t* obar = bars + 3;   // every rank's grid maximum has arrived
   float* W = reinterpret_cast<float*>(rslab);                     // |O_new|^2 on the slice; rslab is idle during C2/D
   const int tmc = lay.tmc;
 
@@ -122,6 +158,13 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     }
   }
   for (int t = tid; t < lay.tmr * lay.tmc; t += NT) Tm[t] = 0u;
+  if (tid == 0) {
+    mbar_init(rbar, 1); mbar_init(cbar, 1); mbar_init(ubar, C); mbar_init(obar, 1);
+  }
+  const uint32_t rbar_a = smem_u32(rbar), cbar_a = smem_u32(cbar), ubar_a = smem_u32(ubar), obar_a = smem_u32(obar);
+  const uint32_t rslab_a = smem_u32(rslab), cslab_a = smem_u32(cslab), pmx_a = smem_u32(pmx), omx_a = smem_u32(omx);
+  const uint32_t rbar_bytes = (uint32_t)(sizeof(float2) * RPC * NC + sizeof(float) * C);
+  const uint32_t cbar_bytes = (uint32_t)(sizeof(float2) * N * ncl);
   cluster.sync();                                          // every CTA is resident and initialised before any remote write
 
   const float kd1 = p.kappa * p.delta1, kd2 = p.kappa * p.delta2;
@@ -134,9 +177,14 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   long long tprev_ = clock64();
 #endif
 
+  short2 cr_next = p.crop[p.slot_begin % p.n_leds];
   for (int u = 0; u < p.n_updates; ++u) {
     const int slot = (p.slot_begin + u) % p.n_leds;
-    const short2 cr = p.crop[slot];
+    const short2 cr = cr_next;
+    {
+      const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
+      cr_next = p.crop[nslot];                              // in flight during this update
+    }
     const int xs = cr.x, ys = cr.y;
     const float* __restrict__ img = stack + (size_t)slot * N * N;
     const int r0 = ys + H + p.ylo, r1 = ys + H + p.yhi, c0 = xs + H + p.xlo, c1 = xs + H + p.xhi;   // rectangle (inclusive)
@@ -147,6 +195,12 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     FPM_TICK(11);
 #endif
 
+    const uint32_t ph = (uint32_t)(u & 1);
+    if (tid == 0) {   // arm this update's transfers (bytes may already be arriving: the counts are signed)
+      mbar_expect_tx(rbar, rbar_bytes);
+      mbar_expect_tx(cbar, cbar_bytes);
+      mbar_expect_tx(obar, (uint32_t)(sizeof(float) * C));
+    }
     if (tid < R1) {   // next LED's 1/I rows of this CTA towards L2: R1 chunks of RPC*R2 floats
       const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
       const float* nx = stack + (size_t)nslot * N * N + ((size_t)tid * N + rank * RPC) * R2;
@@ -162,45 +216,39 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     // ===== S1: pending pupil update (fpmMain.cpp:470-475), Phi = O*P, cols stage A (inverse) on this CTA's columns =====
     {
       float pm2 = 0.f;
-      for (int g = tid; g < R2 * 32; g += NT) {
-        const int i0 = g >> 5, jcl = g & 31;
-        if (jcl < ncl) {
+      for (int g = tid; g < R2 * ncl; g += NT) {        // work items packed densely over the lanes
+        const int i0 = g / ncl, jcl = g - i0 * ncl;
+        {
           float2 v[R1];
-#pragma unroll
-          for (int m = 0; m < R1; ++m) {               // all window loads first: one exposed latency, not R1
-            const int i = i0 + R2 * m;
-            const int iw = (i < H) ? i : i - N;
-            v[m] = (iw >= p.ylo && iw <= p.yhi) ? __ldcg(wrow + (size_t)(iw - p.ylo) * L + jcl) : make_float2(0.f, 0.f);
-          }
-#ifdef FPM_STAGE_TIMING
-#pragma unroll
-          for (int m = 0; m < R1; ++m) asm volatile("" ::"f"(v[m].x), "f"(v[m].y));
-          FPM_TICK(12);
-#endif
+          // Branch-free: rows outside the bbox read a clamped (valid) address and are zeroed afterwards, so the R1
+          // window loads issue back to back and the pupil work below is straight-line code.
 #pragma unroll
           for (int m = 0; m < R1; ++m) {
             const int i = i0 + R2 * m;
             const int iw = (i < H) ? i : i - N;
-            if (iw >= p.ylo && iw <= p.yhi) {
-              const int ir = iw - p.ylo;
-              const float2 O = v[m];
-              const float2 Q = Qc[ir * CPC + jcl];
-              float2 Pv = Pc[ir * CPC + jcl];
-              Pv.x = fmaf(Q.x, inv_objf_max, Pv.x);
-              Pv.y = fmaf(Q.y, inv_objf_max, Pv.y);
-              Pc[ir * CPC + jcl] = Pv;
-              pm2 = fmaxf(pm2, fmaf(Pv.x, Pv.x, Pv.y * Pv.y));
-              v[m] = cmul(O, Pv);
-            }
+            const int irc = min(max(iw - p.ylo, 0), NR - 1);
+            v[m] = wrow[irc * L + jcl];
+          }
+#pragma unroll
+          for (int m = 0; m < R1; ++m) {
+            const int i = i0 + R2 * m;
+            const int iw = (i < H) ? i : i - N;
+            const bool in = (iw >= p.ylo && iw <= p.yhi);
+            const int e = min(max(iw - p.ylo, 0), NR - 1) * CPC + jcl;
+            const float2 Q = Qc[e];
+            float2 Pv = Pc[e];
+            Pv.x = fmaf(Q.x, inv_objf_max, Pv.x);
+            Pv.y = fmaf(Q.y, inv_objf_max, Pv.y);
+            if (in) Pc[e] = Pv;                              // (a clamped row belongs to another work item: read only)
+            const float2 phi = cmul(v[m], Pv);
+            pm2 = in ? fmaxf(pm2, fmaf(Pv.x, Pv.x, Pv.y * Pv.y)) : pm2;
+            v[m] = in ? phi : make_float2(0.f, 0.f);
           }
           fftR<R1, true>(v);
 #pragma unroll
           for (int k1 = 0; k1 < R1; ++k1) cslab[jcl * PR + i0 + R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
         }
       }
-#ifdef FPM_STAGE_TIMING
-      FPM_TICK(13);
-#endif
       pm2 = warp_max(pm2);
       if (lane == 0) red[32 + warp] = pm2;
     }
@@ -209,27 +257,28 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     if (warp == 0) {                                        // this slice's max|P|^2 -> slot [rank] of every CTA
       float m = (lane < NW) ? red[32 + lane] : 0.f;
       m = warp_max(m);
-      if (lane < C) cluster.map_shared_rank(pmx, lane)[rank] = m;
+      if (lane < C) st_async_f1(mapa_u32(pmx_a + 4u * rank, lane), m, mapa_u32(rbar_a, lane));
     }
     // ===== S2: cols stage B (inverse); the results go to the owners of the row positions =====
-    for (int g = tid; g < R1 * 32; g += NT) {
-      const int k1 = g >> 5, jcl = g & 31;
-      if (jcl < ncl) {
+    for (int g = tid; g < R1 * ncl; g += NT) {
+      const int k1 = g / ncl, jcl = g - k1 * ncl;
+      {
         const int js = (p.xlo + jc0 + jcl) & (N - 1);
         float2 v[R2];
 #pragma unroll
         for (int a = 0; a < R2; ++a) v[a] = cslab[jcl * PR + R2 * k1 + a];
         fftR<R2, true>(v);
-        const int pos0 = R2 * k1;
-        float2* dst = cluster.map_shared_rank(rslab, pos0 / RPC) + (pos0 % RPC) * PITCH + js;
+        const int pos0 = R2 * k1, dk = pos0 / RPC;
+        const uint32_t dst = mapa_u32(rslab_a + (uint32_t)(sizeof(float2) * ((pos0 % RPC) * PITCH + js)), dk);
+        const uint32_t dbar = mapa_u32(rbar_a, dk);
 #pragma unroll
-        for (int a = 0; a < R2; ++a) dst[a * PITCH] = v[a];
+        for (int a = 0; a < R2; ++a) st_async_f2(dst + (uint32_t)(sizeof(float2) * a * PITCH), v[a], dbar);
       }
     }
 #ifdef FPM_STAGE_TIMING
     FPM_TICK(14);
 #endif
-    cluster.sync();                                         // #1: row slabs complete
+    mbar_wait_cluster(rbar, ph);                            // row slab complete (every rank's S2 bytes have landed)
     FPM_TICK(2);
     // 1/I of this CTA's S4 work items: issued now, consumed after S3
     constexpr int S4R = (RPC * R1 + NT - 1) / NT;
@@ -311,23 +360,23 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
         const int jw = (R2 * r < H) ? col : col - N;
         if (jw >= p.xlo && jw <= p.xhi) {
           const int jc = jw - p.xlo;
-          const int dk = jc / CPC;
-          cluster.map_shared_rank(cslab, dk)[(jc - dk * CPC) * PR + pos] = v[r];
+          const int dk = (jc * cpc_inv) >> 16;              // jc / CPC (exact for jc < 256, CPC <= 32)
+          st_async_f2(mapa_u32(cslab_a + (uint32_t)(sizeof(float2) * ((jc - dk * CPC) * PR + pos)), dk), v[r], mapa_u32(cbar_a, dk));
         }
       }
     }
 #ifdef FPM_STAGE_TIMING
     FPM_TICK(15);
 #endif
-    cluster.sync();                                         // #2: column slabs complete
+    mbar_wait_cluster(cbar, ph);                            // column slab complete
     FPM_TICK(5);
     float pm2c = pmx[0];                                    // max|P|^2 over the whole pupil (all ranks' slices)
 #pragma unroll
     for (int k = 1; k < C; ++k) pm2c = fmaxf(pm2c, pmx[k]);
     // ===== S6: cols stage B' (forward) =====
-    for (int g = tid; g < R1 * 32; g += NT) {
-      const int k1 = g >> 5, jcl = g & 31;
-      if (jcl < ncl) {
+    for (int g = tid; g < R1 * ncl; g += NT) {
+      const int k1 = g / ncl, jcl = g - k1 * ncl;
+      {
         float2* cp = cslab + jcl * PR + R2 * k1;
         float2 v[R2];
 #pragma unroll
@@ -340,9 +389,9 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     __syncthreads();
     FPM_TICK(6);
     // ===== S7: cols stage A' (forward) -> Phi' in natural row order; only bbox rows are stored =====
-    for (int g = tid; g < R2 * 32; g += NT) {
-      const int q = g >> 5, jcl = g & 31;
-      if (jcl < ncl) {
+    for (int g = tid; g < R2 * ncl; g += NT) {
+      const int q = g / ncl, jcl = g - q * ncl;
+      {
         float2* cp = cslab + jcl * PR;
         float2 v[R1];
 #pragma unroll
@@ -362,31 +411,38 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     {
       const float inv_pmax = rsqrt_fast(pm2c);
       float2* wr = objFc + (size_t)r0 * L + c0 + jc0;
-      constexpr int UN = (N == 256) ? 12 : 6;               // every window row of a warp in flight at once
-      for (int base = warp; base < NR; base += UN * NW) {
+      constexpr int UN = (N == 256) ? 9 : 6;                // window elements in flight per thread
+      const int n = NR * ncl;
+      const int qNT = ncl ? NT / ncl : 0, rNT = ncl ? NT % ncl : 0;     // t += NT without dividing
+      int ir0 = ncl ? tid / ncl : 0, jl0 = ncl ? tid - ir0 * ncl : 0;
+      for (int base = tid; base < n; base += UN * NT) {
         float2 Ov[UN];
+        {
+          int ir = ir0, jl = jl0;
 #pragma unroll
-        for (int k = 0; k < UN; ++k) {
-          const int ir = base + k * NW;
-          Ov[k] = (ir < NR && lane < ncl) ? __ldcg(wr + (size_t)ir * L + lane) : make_float2(0.f, 0.f);
+          for (int k = 0; k < UN; ++k) {
+            Ov[k] = (base + k * NT < n) ? wr[(size_t)ir * L + jl] : make_float2(0.f, 0.f);
+            ir += qNT; jl += rNT;
+            if (jl >= ncl) { jl -= ncl; ++ir; }
+          }
         }
 #pragma unroll
         for (int k = 0; k < UN; ++k) {
-          const int ir = base + k * NW;
-          if (ir < NR && lane < CPC) {
+          if (base + k * NT < n) {
+            const int ir = ir0, lane_c = jl0;
             float a2n = 0.f;
-            if (lane < ncl) {
+            {
               const int iw = p.ylo + ir, i = iw & (N - 1);
-              const int e = ir * CPC + lane;
+              const int e = ir * CPC + lane_c;
               const float2 O = Ov[k];
               const float2 Pv = Pc[e];
-              const float2 d = csub(cslab[lane * PR + i], cmul(O, Pv));           // dPhi = Phi' - Phi
+              const float2 d = csub(cslab[lane_c * PR + i], cmul(O, Pv));         // dPhi = Phi' - Phi
               const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
               const float2 num = cmulc(d, Pv);
               const float A = pa2 + p.delta2;
               const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
               const float2 On = make_float2(O.x + (num.x * A + num.y * kd2) * sc, O.y + (num.y * A - num.x * kd2) * sc);
-              wr[(size_t)ir * L + lane] = On;
+              wr[(size_t)ir * L + lane_c] = On;
               a2n = fmaf(On.x, On.x, On.y * On.y);
               const float oa2 = fmaf(O.x, O.x, O.y * O.y);
               const float2 numq = cmulc(d, O);
@@ -394,8 +450,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
               const float sq = __fdividef(sqrt_fast(oa2) * Sc[e], fmaf(A1, A1, kd1 * kd1));
               Qc[e] = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
             }
-            W[ir * CPC + lane] = a2n;
+            W[ir * CPC + lane_c] = a2n;
           }
+          ir0 += qNT; jl0 += rNT;
+          if (jl0 >= ncl) { jl0 -= ncl; ++ir0; }
         }
       }
     }
@@ -446,6 +504,9 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       }
     }
     __syncthreads();
+#ifdef FPM_STAGE_TIMING
+    FPM_TICK(12);
+#endif
     for (int t = tid; t < ncr * ncc; t += NT) {              // merge into the owners' grids
       const int ta = t / ncc, tb = t - ta * ncc;
       const unsigned v = Tm[ta * tmc + tb];
@@ -455,7 +516,18 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
         atomicMax(reinterpret_cast<unsigned*>(cluster.map_shared_rank(U, a % C)) + (a / C) * gc + cc0 + tb, v);
       }
     }
-    cluster.sync();                                         // #3: grids complete; this update's spectrum stores are ordered
+    __syncthreads();
+    if (tid == 0) {
+      // one cluster-scope release for the whole CTA (cumulative over the barrier above): the merged maxima and this
+      // update's spectrum stores are visible to whoever observes the arrivals
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < C; ++k) mbar_arrive_remote(mapa_u32(ubar_a, k));
+    }
+#ifdef FPM_STAGE_TIMING
+    FPM_TICK(13);
+#endif
+    mbar_wait_cluster(ubar, ph);                            // every rank has merged
     FPM_TICK(9);
     {
       const int nown = (gr - rank + C - 1) / C;
@@ -470,9 +542,9 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     if (warp == 0) {
       float m = (lane < NW) ? red[lane] : 0.f;
       m = warp_max(m);
-      if (lane < C) cluster.map_shared_rank(omx, lane)[rank] = m;
+      if (lane < C) st_async_f1(mapa_u32(omx_a + 4u * rank, lane), m, mapa_u32(obar_a, lane));
     }
-    cluster.sync();                                         // #4
+    mbar_wait_cluster(obar, ph);
     {
       float om2 = omx[0];
 #pragma unroll
