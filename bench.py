@@ -267,6 +267,14 @@ def run_b200(args):
         upd_per_launch = tiles * n_leds * iters
         ach_gbs = bytes_per_update(N) * upd_per_launch / (kernel_ms * 1e-3) / 1e9
         ach_tf = flops_per_update(N) * upd_per_launch / (kernel_ms * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        # (profiles/traffic.json); per launch like `achieved`, scaled by updates when this launch is a different size
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * (upd_per_launch / tj["updates_per_launch"])
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -282,7 +290,7 @@ def run_b200(args):
                     "chunk_tiles": chunk, "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "kernel": "fpm_update_kernel", "kernel_ms_per_launch": kernel_ms,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)", "kernel": "fpm_update_kernel", "kernel_ms_per_launch": kernel_ms,
                          "algorithmic_bytes_per_update": bytes_per_update(N), "updates_per_launch": upd_per_launch,
                          "peak_source": peak_src},
             "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",

@@ -21,11 +21,14 @@
 // S4 runs the last inverse stage, the amplitude replacement (fpmMain.cpp:378-393) and the first forward
 // stage on the same registers; scrambled position p = R2*k1 + k2 holds index k1 + R1*k2, so no reorder
 // pass exists.  Column stages only visit bbox columns; S3 reads bbox columns only (the rest is zero).
-//   C2  object update on the bbox (fpmMain.cpp:406-447); the window O was prefetched into shared memory
-//       during the previous update; Q = pupil-update numerator replaces it in place
-//   D   exact max|objF| (fpmMain.cpp:460,467) from a grid of (2^cs rows x 32 columns) cell maxima: one
-//       warp per touched cell-row refreshes its cells and the row maximum; untouched rows are reused
-//   E   P += Q / max|objF| (fpmMain.cpp:459-475), max|P| and the window of the next LED
+//   C2  object update on the bbox (fpmMain.cpp:406-447).  The window O was staged by TMA (3-D tensor map over
+//       objFc, mbarrier completion) one update ahead; the new values are written into the window buffer, forwarded
+//       into the next LED's window where the two overlap, and go back to objFc with one TMA store.
+//       Q = pupil-update numerator (fpmMain.cpp:459-472) stays in shared memory.
+//   D   exact max|objF| (fpmMain.cpp:460,467) from a grid U of per-cell maxima (2^cs rows x 16 columns): the cells
+//       the rectangle touches are rebuilt from the on-chip new values + the unchanged outside pixels of the edge
+//       cells; the maximum is a flat scan of U.
+//   The pupil update P += Q / max|objF| (fpmMain.cpp:470-475) is applied by the next update's S1 (or the epilogue).
 #pragma once
 #include <cuda.h>            // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
@@ -56,7 +59,7 @@ struct UpdateParams {
   float delta1, delta2, eps, kappa;
   int ylo, yhi, xlo, xhi;   // support bbox (wrapped)
   int ocp;                  // row pitch (float2) of the on-chip window copies: even and >= NC+1 (TMA boxes start on 16 B)
-  int cs;                   // log2 rows per max-cell (cells are (1<<cs) rows x 32 columns)
+  int cs;                   // log2 rows per max-cell (cells are (1<<cs) rows x 16 columns)
   long long* stage_clk;     // [16] per-stage cycle totals of CTA 0 (only with -DFPM_STAGE_TIMING)
 };
 
