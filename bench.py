@@ -246,15 +246,22 @@ def run_b200(args):
         ctx.finalize(0, nl, sp)
     f1.record(main)
     torch.cuda.synchronize()
-    t_g = time.perf_counter()
+    gather_ms = 0.0
     if world > 1:
         dev_out = ctx.objcrop_tensor(0, nl) if nl else torch.empty((0, L * L * 2), dtype=torch.float32, device="cuda")
-        full = sharding.gather_tiles(dev_out, fov_tiles, rank, world)     # NCCL send/recv -> rank 0
-        torch.cuda.synchronize()
-        del full
-    gather_s = time.perf_counter() - t_g
+        # first pass untimed (NCCL sets its point-to-point channels up lazily), second pass timed on the device
+        for timed in (False, True):
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            full = sharding.gather_tiles(dev_out, fov_tiles, rank, world)     # NCCL send/recv -> rank 0
+            g1.record()
+            torch.cuda.synchronize()
+            del full
+            if timed:
+                gather_ms = g0.elapsed_time(g1)
     fov_ms = sharding.max_over_ranks(f0.elapsed_time(f1), "cuda")
-    gather_s = sharding.max_over_ranks(gather_s, "cuda")
+    gather_s = sharding.max_over_ranks(gather_ms, "cuda") * 1e-3
 
     if rank == 0:
         peaks = {}
