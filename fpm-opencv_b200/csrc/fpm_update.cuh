@@ -215,6 +215,13 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     }
     return half_warp_max(cm, lane);
   };
+  // Row passes: work item g = tid + q*NT owns row g % N = tid % N (NT is a multiple of N), so the warps
+  // {w : w % (N/32) == b} own the 32 rows of block b in S3, S4 and S5 alike: a named barrier over those
+  // NT/N warps replaces the block-wide barrier between the row stages.
+  static_assert(NT % N == 0 && N % 32 == 0 && N / 32 <= 15, "row-block barriers");
+  auto row_block_sync = [&]() {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp % (N / 32))), "r"(NT / N * 32) : "memory");
+  };
   // ---- prologue: tables, pupil -> shared memory, max|P|^2, max-cell grid, first window ----
   for (int t = tid; t < N; t += NT) {
     const int b = t / R2, a = t % R2;
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
 #pragma unroll
       for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
     }
-    __syncthreads();
+    row_block_sync();          // S3 -> S4 -> S5 exchange data only within a block of 32 rows (= NT/N warps)
     FPM_TICK(3);
     // ===== S4: rows stage B (inverse) + amplitude replacement + rows stage B' (forward) =====
     constexpr int S4R = (N * R1 + NT - 1) / NT;                 // work items per thread
@@ -395,7 +402,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
 #pragma unroll
       for (int q = 0; q < R2; ++q) rp[q] = twmul<false>(v[q], twB[q * R1 + k1]);
     }
-    __syncthreads();
+    row_block_sync();
     FPM_TICK(4);
     // ================= S5: rows stage A' (forward) =================
     for (int g = tid; g < N * R2; g += NT) {
