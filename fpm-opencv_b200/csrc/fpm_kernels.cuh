@@ -6,6 +6,7 @@
 #include "fft_regs.cuh"
 #include "fpm_update.cuh"
 #include "fpm_update_cluster.cuh"
+#include "fpm_general.cuh"
 
 namespace fpm {
 

@@ -64,6 +64,13 @@ struct fpmb200_ctx {
   CUtensorMap tmap;            // objFc as (2*L, L, n_tiles) floats with a (2*ocp, NR, 1) box
   bool have_tmap = false;
   int ocp = 0;
+  // general (unfused) path for tile sizes other than 64/128/256
+  bool general = false;
+  float2* gfield = nullptr;    // [n_tiles][N][N]
+  float2* gq = nullptr;        // [n_tiles][N][N]
+  float* gcells = nullptr;     // [n_tiles][cgr][cgc]
+  float* gscal = nullptr;      // [n_tiles][4]
+  int cgr = 0, cgc = 0;
   int cluster_req = 0;         // CTAs per tile asked for (0 = choose)
   int cluster = 1;             // CTAs per tile in use (1 = fpm_update_kernel, >1 = fpm_update_cluster_kernel)
   int cpc = 0;                 // bbox columns per CTA of the cluster kernel
@@ -109,6 +116,8 @@ static cudaError_t copy_sync(fpmb200_ctx* c, void* dst, const void* src, size_t 
 static void free_tiles(fpmb200_ctx* c) {
   cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->raw); cudaFree(c->support);
   cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch); cudaFree(c->qbuf);
+  cudaFree(c->gfield); cudaFree(c->gq); cudaFree(c->gcells); cudaFree(c->gscal);
+  c->gfield = c->gq = nullptr; c->gcells = c->gscal = nullptr; c->general = false;
   c->objFc = c->objCrop = c->pupil = c->twN = c->twL = c->field_gmem = c->scratch = c->qbuf = nullptr;
   c->stack = nullptr; c->raw = nullptr; c->support = nullptr; c->crop = nullptr;
   c->have_leds = c->have_support = c->have_stack = false;
@@ -140,18 +149,17 @@ static int upload_twiddles(fpmb200_ctx* c, float2* dst, int n) {
 extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlarge, int n_leds) {
   if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
   if (n_tiles <= 0 || n_leds <= 0) return fail(FPMB200_ERR_ARG, "n_tiles and n_leds must be positive");
-  if (Np != 64 && Np != 128 && Np != 256)
-    return fail(FPMB200_ERR_ARG, "Np=%d unsupported: the fused tile FFT handles 64, 128 and 256", Np);
-  if (Nlarge < Np || Nlarge % 64 != 0 || Nlarge > 8192)
-    return fail(FPMB200_ERR_ARG, "Nlarge=%d must be a multiple of 64 in [Np, 8192]", Nlarge);
-  {
-    int r = Nlarge;
-    for (int f : {2, 3, 5}) while (r % f == 0) r /= f;
-    if (r != 1) return fail(FPMB200_ERR_ARG, "Nlarge=%d has a prime factor other than 2,3,5", Nlarge);
-  }
+  auto smooth235 = [](int v) { for (int f : {2, 3, 5}) while (v % f == 0) v /= f; return v == 1; };
+  if (Np < 8 || Np > 1024 || (Np & 1) || !smooth235(Np))
+    return fail(FPMB200_ERR_ARG, "Np=%d unsupported: even, 8..1024, prime factors 2,3,5 only (fused kernels: 64, 128, 256)", Np);
+  if (Nlarge < Np || Nlarge > 3584 || (Nlarge & 1) || !smooth235(Nlarge))
+    return fail(FPMB200_ERR_ARG, "Nlarge=%d must be even, in [Np, 3584], with prime factors 2,3,5 only", Nlarge);
+  // the fused kernels need power-of-two tiles and 64-aligned spectra; everything else takes the general path
+  const bool general = !((Np == 64 || Np == 128 || Np == 256) && Nlarge % 64 == 0);
   CK(cudaSetDevice(c->device));
   free_tiles(c);
   c->n_tiles = n_tiles; c->N = Np; c->L = Nlarge; c->n_leds = n_leds;
+  c->general = general;
   const size_t LL = (size_t)Nlarge * Nlarge, NN = (size_t)Np * Np;
   CK(cudaMalloc(&c->objFc, sizeof(float2) * LL * n_tiles));
   CK(cudaMalloc(&c->objCrop, sizeof(float2) * LL * n_tiles));
@@ -280,6 +288,24 @@ static int select_variant(fpmb200_ctx* c) {
   const int N = c->N;
   const int ylo = c->ylo, yhi = c->yhi, xlo = c->xlo, xhi = c->xhi;
   CK(cudaSetDevice(c->device));
+  if (c->general) {
+    if (c->cluster_req > 1) return fail(FPMB200_ERR_ARG, "cluster kernels exist for Np = 128 and 256 only (Np=%d)", N);
+    c->cluster = 1;
+    c->cgr = c->cgc = (c->L + 15) / 16;
+    if (!c->gfield) {
+      const size_t NN = (size_t)N * N;
+      CK(cudaMalloc(&c->gfield, sizeof(float2) * NN * c->n_tiles));
+      CK(cudaMalloc(&c->gq, sizeof(float2) * NN * c->n_tiles));
+      CK(cudaMalloc(&c->gcells, sizeof(float) * (size_t)c->cgr * c->cgc * c->n_tiles));
+      CK(cudaMalloc(&c->gscal, sizeof(float) * 4 * c->n_tiles));
+      CK(cudaMemsetAsync(c->gq, 0, sizeof(float2) * NN * c->n_tiles, c->stream));
+      CK(cudaMemsetAsync(c->gscal, 0, sizeof(float) * 4 * c->n_tiles, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    snprintf(c->variant, sizeof c->variant,
+             "general path (unfused: line_fft_kernel + 6 elementwise kernels per update) Np=%d Nlarge=%d maxcell=16x16", N, c->L);
+    return FPMB200_OK;
+  }
   // A 256x256 field does not fit one SM: spread the tile over a cluster of 8 CTAs (field, pupil and pupil increment on
   // chip, transposes through DSMEM).  128x128 tiles use a cluster only on request (fpmb200_set_cluster).
   c->cluster = 1;
@@ -371,7 +397,10 @@ extern "C" int fpmb200_upload_stack(fpmb200_ctx* c, int first, int n, const uint
   // once per upload: uint16 -> 1/I (float) in the layout the update kernel streams (stack_offset<N>)
   const long long first_img = (long long)first * c->n_leds;
   const int n_img = n * c->n_leds;
-  switch (c->N) {
+  if (c->general) {
+    const long long n_el = (long long)n_img * c->N * c->N;
+    stack_convert_general<<<(int)((n_el + 256 * 8 - 1) / (256 * 8)), 256, 0, st>>>(c->stack, c->raw, first_img * c->N * c->N, n_el);
+  } else switch (c->N) {
     case 64: stack_convert_kernel<64><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
     case 128: stack_convert_kernel<128><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
     case 256: stack_convert_kernel<256><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
@@ -424,7 +453,8 @@ extern "C" int fpmb200_init_tiles(fpmb200_ctx* c, int first, int n, int init_slo
   const int batch_max = (int)(c->scratch_elems / ((size_t)N * N));
   for (int t0 = first; t0 < first + n; t0 += batch_max) {
     const int b = (first + n - t0) < batch_max ? (first + n - t0) : batch_max;
-    switch (N) {
+    if (c->general) gen_init_amp<<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0, N);
+    else switch (N) {
       case 64: init_amp_kernel<64><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
       case 128: init_amp_kernel<128><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
       case 256: init_amp_kernel<256><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
@@ -467,8 +497,51 @@ static int launch_cluster(fpmb200_ctx* c, const UpdateParams& p, int n_tiles, cu
   return FPMB200_OK;
 }
 
+template <bool INV>
+static int fft2d(fpmb200_ctx* c, float2* data, int n, const float2* tw, int batch, long long batch_stride, float scale,
+                 cudaStream_t st);
+
+// The unfused path (csrc/fpm_general.cuh): 11 launches per update, every launch covers tiles [first, first+n).
+static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
+  GeneralParams p;
+  memset(&p, 0, sizeof p);
+  const int N = c->N;
+  p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop;
+  p.field = c->gfield; p.q = c->gq; p.cells = c->gcells; p.scal = c->gscal;
+  p.N = N; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first; p.cgr = c->cgr; p.cgc = c->cgc;
+  p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
+  const int bx = (N * N + 255) / 256 < 64 ? (N * N + 255) / 256 : 64;
+  const dim3 ge(bx, n);
+  const int tc = (N + 15) / 16 + 1;                              // cells a window can touch per dimension
+  float2* fld = c->gfield + (size_t)first * N * N;
+  // state the loop carries in scal: max|P|^2 of the current pupil; the cell grid of the current spectrum
+  p.apply = 1; p.slot = 0;
+  gen_cells_update<<<dim3(c->cgr * c->cgc, n), 256, 0, st>>>(p, 1);
+  gen_cells_max<<<n, 256, 0, st>>>(p);
+  p.apply = 0;
+  gen_pupil_update<<<ge, 256, 0, st>>>(p);
+  c->launches += 3;
+  p.apply = 1;
+  int rc;
+  for (int u = 0; u < n_updates; ++u) {
+    p.slot = (slot_begin + u) % c->n_leds;
+    gen_window_mul<<<ge, 256, 0, st>>>(p);
+    if ((rc = fft2d<true>(c, fld, N, c->twN, n, (long long)N * N, 1.f / ((float)N * (float)N), st))) return rc;
+    gen_amplitude<<<ge, 256, 0, st>>>(p);
+    if ((rc = fft2d<false>(c, fld, N, c->twN, n, (long long)N * N, 1.f, st))) return rc;
+    gen_object_update<<<ge, 256, 0, st>>>(p);
+    gen_cells_update<<<dim3(tc * tc, n), 256, 0, st>>>(p, 0);
+    gen_cells_max<<<n, 256, 0, st>>>(p);
+    gen_pupil_update<<<ge, 256, 0, st>>>(p);
+    c->launches += 6;
+  }
+  CK(cudaGetLastError());
+  return FPMB200_OK;
+}
+
 static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
   if (!c->have_support || !c->have_leds) return fail(FPMB200_ERR_STATE, "upload LED tables and the pupil support first");
+  if (c->general) { CK(cudaSetDevice(c->device)); return run_updates_general(c, first, n, slot_begin, n_updates, st); }
   UpdateParams p;
   memset(&p, 0, sizeof p);
   p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop;

@@ -143,6 +143,52 @@ def test_against_committed_opencv_fixtures(path):
     ctx.close()
 
 
+# ---- the shipped JSONs with their literal cropSizeX (90, 100, 200): general, unfused path ---------
+@pytest.mark.parametrize("name,n_leds,iters", [("cfg7_mono_np90", 117, 3), ("cfg8_cellScope_np100", 60, 2),
+                                               ("cfg4s_dogStomach_np200", 40, 2)])
+@pytest.mark.parametrize("kappa", [1, 0])
+def test_literal_tile_sizes(name, n_leds, iters, kappa):
+    """Np = 90 / 100 / 200 (Nlarge 360 / 600 / 600): mixed-radix transforms, cells of the max grid cut by the spectrum
+    border.  Per-step parity from the oracle's state for the first LEDs, then a full run."""
+    c = T.case(name, n_leds=n_leds)
+    ctx = c.make_ctx(kappa=kappa)
+    assert "general path" in ctx.variant
+    st = orc.init_state(c.stack, c.L, c.r)
+    gF, _, gP = ctx.download(0, objCrop=False)
+    assert orc.rel_l2(gF, T.corner(st.objFc)) < 1e-6 and np.array_equal(gP, st.P.astype(np.complex64))
+    for k in range(len(c.cx)):
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, kappa)
+    worst = 0.0
+    for k in range(min(12, len(c.cx))):
+        ctx.upload_state(0, T.corner(st.objFc), st.P)
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, kappa)
+        ctx.step(0, k)
+        worst = max(worst, *compare(ctx, st, tol=STEP_TOL, crop=False))
+    ctx.init_tiles()
+    ctx.run(iters)
+    ctx.finalize()
+    e = compare(ctx, c.oracle_run(iters, kappa=kappa))
+    print("%s kappa=%d per-step %.2e, %d iterations: objF %.2e pupil %.2e" % (name, kappa, worst, iters, e[0], e[1]))
+    ctx.close()
+
+
+def test_general_path_many_tiles():
+    """Batched over tiles: identical inputs -> identical bits in every slot; sub-ranges of tiles are independent."""
+    c = T.Case("cfg7_mono_np90", 11, 20)
+    a = c.make_ctx(n_tiles=5)
+    a.run(2, 0, 5)
+    b = c.make_ctx(n_tiles=5)
+    b.run(2, 0, 2)
+    b.run(2, 2, 3)
+    ref = a.download(0, objCrop=False)
+    for t in range(5):
+        for ctx in (a, b):
+            for x, y in zip(ctx.download(t, objCrop=False), ref):
+                if x is not None:
+                    assert np.array_equal(x, y)
+    a.close(), b.close()
+
+
 # ---- structure / edge cases ----------------------------------------------------------------------
 def test_dense_support_uses_general_path():
     """A support mask covering the whole window: no bbox pruning, pupil kept in global memory at
