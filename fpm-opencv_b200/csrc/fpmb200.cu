@@ -71,6 +71,15 @@ struct fpmb200_ctx {
   float* gcells = nullptr;     // [n_tiles][cgr][cgc]
   float* gscal = nullptr;      // [n_tiles][4]
   int cgr = 0, cgc = 0;
+  // full-FOV helpers (csrc/fpm_fov.cuh)
+  int2* origins = nullptr;     // [n_tiles] ROI origin of every tile in the camera frame
+  bool have_origins = false;
+  uint16_t* frame_dev = nullptr;
+  size_t frame_elems = 0;
+  int* bg_dev = nullptr;       // [n_leds] background value subtracted from each LED frame
+  int origin_max_x = 0, origin_max_y = 0;
+  float* mosaic_dev = nullptr;
+  size_t mosaic_elems = 0;
   int cluster_req = 0;         // CTAs per tile asked for (0 = choose)
   int cluster = 1;             // CTAs per tile in use (1 = fpm_update_kernel, >1 = fpm_update_cluster_kernel)
   int cpc = 0;                 // bbox columns per CTA of the cluster kernel
@@ -117,6 +126,9 @@ static void free_tiles(fpmb200_ctx* c) {
   cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->raw); cudaFree(c->support);
   cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch); cudaFree(c->qbuf);
   cudaFree(c->gfield); cudaFree(c->gq); cudaFree(c->gcells); cudaFree(c->gscal);
+  cudaFree(c->origins); cudaFree(c->frame_dev); cudaFree(c->bg_dev); cudaFree(c->mosaic_dev);
+  c->origins = nullptr; c->frame_dev = nullptr; c->bg_dev = nullptr; c->mosaic_dev = nullptr;
+  c->have_origins = false; c->frame_elems = c->mosaic_elems = 0;
   c->gfield = c->gq = nullptr; c->gcells = c->gscal = nullptr; c->general = false;
   c->objFc = c->objCrop = c->pupil = c->twN = c->twL = c->field_gmem = c->scratch = c->qbuf = nullptr;
   c->stack = nullptr; c->raw = nullptr; c->support = nullptr; c->crop = nullptr;
@@ -653,9 +665,108 @@ extern "C" int fpmb200_device_buffer(fpmb200_ctx* c, int which, int tile, void**
     case 1: b = sizeof(float2) * LL; *ptr = c->objCrop + LL * tile; break;
     case 2: b = sizeof(float2) * NN; *ptr = c->pupil + NN * tile; break;
     case 3: b = sizeof(float) * NN * c->n_leds; *ptr = c->stack + NN * c->n_leds * tile; break;
-    default: return fail(FPMB200_ERR_ARG, "which=%d not in 0..3", which);
+    case 4: b = sizeof(uint16_t) * NN * c->n_leds; *ptr = c->raw + NN * c->n_leds * tile; break;
+    default: return fail(FPMB200_ERR_ARG, "which=%d not in 0..4", which);
   }
   if (bytes) *bytes = b;
+  return FPMB200_OK;
+}
+
+// ---- full field of view: frame ingest and mosaic ---------------------------------------
+extern "C" int fpmb200_set_tile_origins(fpmb200_ctx* c, const int32_t* x, const int32_t* y, int n_tiles) {
+  if (!c || !x || !y) return fail(FPMB200_ERR_ARG, "NULL argument");
+  if (!c->n_tiles) return fail(FPMB200_ERR_STATE, "fpmb200_tiles_alloc first");
+  if (n_tiles != c->n_tiles) return fail(FPMB200_ERR_ARG, "n_tiles=%d differs from the allocation (%d)", n_tiles, c->n_tiles);
+  std::vector<int2> h(n_tiles);
+  for (int t = 0; t < n_tiles; ++t) {
+    if (x[t] < 0 || y[t] < 0) return fail(FPMB200_ERR_ARG, "tile %d: negative ROI origin (%d,%d)", t, x[t], y[t]);
+    h[t] = make_int2(x[t], y[t]);
+  }
+  CK(cudaSetDevice(c->device));
+  if (!c->origins) CK(cudaMalloc(&c->origins, sizeof(int2) * n_tiles));
+  if (!c->bg_dev) { CK(cudaMalloc(&c->bg_dev, sizeof(int) * c->n_leds)); CK(cudaMemsetAsync(c->bg_dev, 0, sizeof(int) * c->n_leds, c->stream)); }
+  CK(copy_sync(c, c->origins, h.data(), sizeof(int2) * n_tiles, cudaMemcpyHostToDevice));
+  c->have_origins = true;
+  // the largest ROI corner, checked against every frame
+  c->origin_max_x = 0; c->origin_max_y = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    if (x[t] > c->origin_max_x) c->origin_max_x = x[t];
+    if (y[t] > c->origin_max_y) c->origin_max_y = y[t];
+  }
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_ingest_frame(fpmb200_ctx* c, int led_slot, const uint16_t* frame, int width, int height, int divisor,
+                                    int bk1x, int bk1y, int bk2x, int bk2y, int bg_threshold, void* stream) {
+  if (!c || !frame) return fail(FPMB200_ERR_ARG, "NULL argument");
+  if (!c->have_origins) return fail(FPMB200_ERR_STATE, "fpmb200_set_tile_origins first");
+  if (led_slot < 0 || led_slot >= c->n_leds) return fail(FPMB200_ERR_ARG, "led_slot %d outside [0,%d)", led_slot, c->n_leds);
+  const int Np = c->N;
+  auto inside = [&](int x, int y) { return x >= 0 && y >= 0 && x + Np <= width && y + Np <= height; };
+  if (width <= 0 || height <= 0 || !inside(c->origin_max_x, c->origin_max_y) || !inside(bk1x, bk1y) || !inside(bk2x, bk2y))
+    return fail(FPMB200_ERR_ARG, "a tile or background ROI leaves the %dx%d frame", width, height);
+  if (divisor < 0) return fail(FPMB200_ERR_ARG, "divisor < 0");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const size_t elems = (size_t)width * height;
+  if (elems > c->frame_elems) {
+    CK(cudaStreamSynchronize(st));
+    cudaFree(c->frame_dev);
+    c->frame_dev = nullptr; c->frame_elems = 0;
+    CK(cudaMalloc(&c->frame_dev, sizeof(uint16_t) * elems));
+    c->frame_elems = elems;
+  }
+  CK(cudaMemcpyAsync(c->frame_dev, frame, sizeof(uint16_t) * elems, cudaMemcpyHostToDevice, st));
+  ingest_bg_kernel<<<1, 1024, 0, st>>>(c->frame_dev, width, Np, bk1x, bk1y, bk2x, bk2y, bg_threshold, c->bg_dev + led_slot);
+  const int R1 = c->general ? 1 : (Np == 64 ? 8 : 16);
+  const int bx = (Np * Np + 255) / 256 < 16 ? (Np * Np + 255) / 256 : 16;
+  ingest_tiles_kernel<<<dim3(bx, c->n_tiles), 256, 0, st>>>(c->frame_dev, width, c->origins, 0, c->raw, c->stack, c->n_leds,
+                                                             led_slot, Np, R1, c->general ? 0 : 1, divisor, c->bg_dev + led_slot);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  c->have_stack = true;
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_ingest_bg(fpmb200_ctx* c, int32_t* bg_val) {
+  if (!c || !bg_val) return fail(FPMB200_ERR_ARG, "NULL argument");
+  if (!c->bg_dev) return fail(FPMB200_ERR_STATE, "no frame ingested yet");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  CK(copy_sync(c, bg_val, c->bg_dev, sizeof(int) * c->n_leds, cudaMemcpyDeviceToHost));
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_mosaic(fpmb200_ctx* c, const void* tiles_device, int nx, int ny, int step, float* out, int out_on_device,
+                              void* stream) {
+  if (!c || !out) return fail(FPMB200_ERR_ARG, "NULL argument");
+  if (!c->n_tiles) return fail(FPMB200_ERR_STATE, "fpmb200_tiles_alloc first");
+  if (nx <= 0 || ny <= 0 || step <= 0 || step > c->N) return fail(FPMB200_ERR_ARG, "need nx, ny > 0 and 0 < step <= Np");
+  if (!tiles_device && nx * ny > c->n_tiles) return fail(FPMB200_ERR_ARG, "%dx%d tiles exceed the allocation (%d)", nx, ny, c->n_tiles);
+  if (c->L % c->N) return fail(FPMB200_ERR_ARG, "Nlarge is not a multiple of Np");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  MosaicParams p;
+  p.tiles = tiles_device ? (const float2*)tiles_device : c->objCrop;
+  p.L = c->L; p.Np = c->N; p.step = step; p.nx = nx; p.ny = ny;
+  const int f = c->L / c->N;
+  p.Wm = ((nx - 1) * step + c->N) * f; p.Hm = ((ny - 1) * step + c->N) * f;
+  const size_t elems = (size_t)p.Wm * p.Hm;
+  if (out_on_device) p.out = out;
+  else {
+    if (elems > c->mosaic_elems) {
+      CK(cudaStreamSynchronize(st));
+      cudaFree(c->mosaic_dev);
+      c->mosaic_dev = nullptr; c->mosaic_elems = 0;
+      CK(cudaMalloc(&c->mosaic_dev, sizeof(float) * elems));
+      c->mosaic_elems = elems;
+    }
+    p.out = c->mosaic_dev;
+  }
+  mosaic_kernel<<<c->sm_count * 8, 256, 0, st>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  if (!out_on_device) CK(cudaMemcpyAsync(out, c->mosaic_dev, sizeof(float) * elems, cudaMemcpyDeviceToHost, st));
   return FPMB200_OK;
 }
 

@@ -52,6 +52,10 @@ def load():
         "fpmb200_download": (i, [vp, i, vp, vp, vp]),
         "fpmb200_download_objcrop": (i, [vp, i, i, vp, vp]),
         "fpmb200_device_buffer": (i, [vp, i, i, C.POINTER(vp), C.POINTER(C.c_ulonglong)]),
+        "fpmb200_set_tile_origins": (i, [vp, vp, vp, i]),
+        "fpmb200_ingest_frame": (i, [vp, i, vp, i, i, i, i, i, i, i, i, vp]),
+        "fpmb200_ingest_bg": (i, [vp, vp]),
+        "fpmb200_mosaic": (i, [vp, vp, i, i, i, vp, i, vp]),
         "fpmb200_sync": (i, [vp]),
         "fpmb200_kernel_launches": (C.c_longlong, [vp]),
         "fpmb200_variant": (C.c_char_p, [vp]),
@@ -67,7 +71,8 @@ EXPORTS = ["fpmb200_last_error", "fpmb200_abi_version", "fpmb200_create", "fpmb2
            "fpmb200_tiles_alloc", "fpmb200_set_params", "fpmb200_set_cluster", "fpmb200_upload_leds",
            "fpmb200_upload_pupil_support", "fpmb200_upload_stack", "fpmb200_init_tiles", "fpmb200_run",
            "fpmb200_step", "fpmb200_finalize", "fpmb200_upload_state", "fpmb200_download",
-           "fpmb200_download_objcrop", "fpmb200_device_buffer", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
+           "fpmb200_download_objcrop", "fpmb200_device_buffer", "fpmb200_set_tile_origins", "fpmb200_ingest_frame",
+           "fpmb200_ingest_bg", "fpmb200_mosaic", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
 
 
 class FpmError(RuntimeError):
@@ -134,6 +139,41 @@ class Context:
 
     def upload_stack_ptr(self, tile_first, n, host_ptr, stream=None):
         self._ck(self.L.fpmb200_upload_stack(self._h, tile_first, n, C.c_void_p(host_ptr), stream))
+
+    def set_tile_origins(self, xs, ys):
+        x = np.ascontiguousarray(xs, dtype=np.int32)
+        y = np.ascontiguousarray(ys, dtype=np.int32)
+        self._ck(self.L.fpmb200_set_tile_origins(self._h, _ptr(x), _ptr(y), len(x)))
+
+    def ingest_frame(self, led_slot, frame, divisor, bk1, bk2, bg_threshold, stream=None):
+        f = np.ascontiguousarray(frame, dtype=np.uint16)
+        self._ck(self.L.fpmb200_ingest_frame(self._h, int(led_slot), _ptr(f), f.shape[1], f.shape[0], int(divisor),
+                                             int(bk1[0]), int(bk1[1]), int(bk2[0]), int(bk2[1]), int(bg_threshold), stream))
+        if stream is None:
+            self.sync()          # `f` may be a temporary
+
+    def ingest_bg(self):
+        out = np.zeros(self.n_leds, np.int32)
+        self._ck(self.L.fpmb200_ingest_bg(self._h, _ptr(out)))
+        return out
+
+    def raw_stack(self, tile):
+        """uint16 stack of one tile as uploaded / ingested, [n_leds][Np][Np] (device -> host via torch-free memcpy)."""
+        import ctypes
+        ptr, nbytes = self.device_buffer(4, tile)
+        out = np.empty((self.n_leds, self.Np, self.Np), np.uint16)
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        self.sync()
+        assert rt.cudaMemcpy(_ptr(out), ctypes.c_void_p(ptr), nbytes, 2) == 0
+        return out
+
+    def mosaic(self, nx, ny, step):
+        f = self.Nlarge // self.Np
+        out = np.empty((((ny - 1) * step + self.Np) * f, ((nx - 1) * step + self.Np) * f), np.float32)
+        self._ck(self.L.fpmb200_mosaic(self._h, None, nx, ny, step, _ptr(out), 0, None))
+        self.sync()
+        return out
 
     def init_tiles(self, tile_first=0, n=None, init_led_slot=1, stream=None):
         self._ck(self.L.fpmb200_init_tiles(self._h, tile_first, self.n_tiles - tile_first if n is None else n,

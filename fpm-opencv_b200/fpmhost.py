@@ -28,7 +28,8 @@ class Led(C.Structure):
 
 EXPORTS = ["fpmhost_last_error", "fpmhost_open", "fpmhost_close", "fpmhost_geometry", "fpmhost_load",
            "fpmhost_get_scalars", "fpmhost_get_order", "fpmhost_get_led", "fpmhost_get_image",
-           "fpmhost_geometry_source", "fpmhost_pupil_support", "fpmhost_device_from_env"]
+           "fpmhost_geometry_source", "fpmhost_pupil_support", "fpmhost_preprocess_frame", "fpmhost_tile_grid",
+           "fpmhost_device_from_env"]
 
 
 def lib_path():
@@ -55,6 +56,8 @@ def load():
         L.fpmhost_geometry_source.argtypes = [vp]
         L.fpmhost_geometry_source.restype = C.c_char_p
         L.fpmhost_pupil_support.argtypes = [i, i, vp]
+        L.fpmhost_preprocess_frame.argtypes = [vp] + [i] * 11 + [vp, vp]
+        L.fpmhost_tile_grid.argtypes = [i, i, i, i, vp, vp]
         _lib = L
     return _lib
 
@@ -127,3 +130,29 @@ def pupil_support(Np, radius):
     m = np.zeros((Np, Np), np.float32)
     load().fpmhost_pupil_support(Np, radius, C.c_void_p(m.ctypes.data))
     return m
+
+
+def preprocess_frame(frame, Np, crop, bk1, bk2, divisor, bg_threshold):
+    """loadFPMDataset's per-frame preprocessing (fpmMain.cpp:124-144) -> (image [Np][Np] uint16, bg_val)."""
+    f = np.ascontiguousarray(frame, dtype=np.uint16)
+    out = np.zeros((Np, Np), np.uint16)
+    bg = C.c_int(0)
+    L = load()
+    rc = L.fpmhost_preprocess_frame(C.c_void_p(f.ctypes.data), f.shape[1], f.shape[0], Np, int(crop[0]), int(crop[1]),
+                                    int(bk1[0]), int(bk1[1]), int(bk2[0]), int(bk2[1]), int(divisor), int(bg_threshold),
+                                    C.c_void_p(out.ctypes.data), C.byref(bg))
+    if rc != 0:
+        raise RuntimeError("fpmhost_preprocess_frame: " + L.fpmhost_last_error().decode())
+    return out, bg.value
+
+
+def tile_grid(width, height, Np, overlap=0):
+    """(nx, ny, xs, ys): regular grid of tile ROI origins, tile index = iy*nx + ix."""
+    nx, ny = C.c_int(0), C.c_int(0)
+    L = load()
+    if L.fpmhost_tile_grid(width, height, Np, overlap, C.byref(nx), C.byref(ny)) != 0:
+        raise RuntimeError("fpmhost_tile_grid: " + L.fpmhost_last_error().decode())
+    step = Np - overlap
+    xs = np.tile(np.arange(nx.value) * step, ny.value).astype(np.int32)
+    ys = np.repeat(np.arange(ny.value) * step, nx.value).astype(np.int32)
+    return nx.value, ny.value, xs, ys

@@ -257,7 +257,7 @@ bool preprocessFrame(const FPM_Dataset& d, const uint16_t* frame, int w, int h, 
   const double bk1 = roiMean(d.bk1cropX, d.bk1cropY), bk2 = roiMean(d.bk2cropX, d.bk2cropY);  // :131-134
   double bg_val = (bk2 + bk1) / 2;                                                            // :136-138
   if (bg_val > d.bgThreshold) bg_val = d.bgThreshold;
-  im->bg_val = (int16_t)std::round(bg_val);                                                   // :140
+  im->bg_val = (int16_t)(int)std::round(bg_val);                                              // :140
   for (auto& p : im->Image) {                                                                 // :143-144 saturating
     int v = (int)p - (int)im->bg_val;
     p = (uint16_t)(v < 0 ? 0 : v > 65535 ? 65535 : v);
@@ -340,6 +340,12 @@ int16_t loadFPMDataset(FPM_Dataset* d) {
   }
   sortLedOrder(d);
   return 1;
+}
+
+void tileGrid(int width, int height, int Np, int overlap, int* nx, int* ny) {
+  const int step = Np - overlap;
+  *nx = (width - Np) / step + 1;
+  *ny = (height - Np) / step + 1;
 }
 
 void makePupilSupport(int Np, int radius, std::vector<float>* mask) {

@@ -89,6 +89,8 @@ int16_t loadFPMDataset(FPM_Dataset* dataset);   // fpmMain.h:118
 void runFPM(FPM_Dataset* dataset);              // fpmMain.h:119
 
 // filled disc of cv::circle(centre (Np/2,Np/2), radius, filled) then fftShift (fpmMain.cpp:304-313)
+// regular tile grid over a frame: counts of tiles with ROI origin (ix*(Np-overlap), iy*(Np-overlap))
+void tileGrid(int width, int height, int Np, int overlap, int* nx, int* ny);
 void makePupilSupport(int Np, int radius, std::vector<float>* mask);
 // parses OPENCV_OPENCL_DEVICE as exported by use_gpu.sh / use_cpu.sh: returns CUDA ordinal >= 0,
 // -1 for "CPU:*" (not served by this build), 0 when unset.

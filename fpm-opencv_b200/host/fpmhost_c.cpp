@@ -107,4 +107,28 @@ extern "C" int fpmhost_pupil_support(int Np, int radius, float* mask) {
   return 0;
 }
 
+extern "C" int fpmhost_preprocess_frame(const uint16_t* frame, int width, int height, int Np, int cropX, int cropY, int bk1x,
+                                        int bk1y, int bk2x, int bk2y, int divisor, int bgThreshold, uint16_t* out,
+                                        int* bg_val) {
+  if (!frame || !out) return fail(-1, "bad argument");
+  FPM_Dataset d;
+  d.Np = Np; d.cropX = cropX; d.cropY = cropY; d.bk1cropX = bk1x; d.bk1cropY = bk1y; d.bk2cropX = bk2x; d.bk2cropY = bk2y;
+  d.bgThreshold = bgThreshold;
+  d.darkfieldExpMultiplier = divisor;           // applied when illumination_na > objectiveNA (fpmMain.cpp:128)
+  d.objectiveNA = 0.f;
+  FPMimg im;
+  im.illumination_na = 1.f;
+  std::string err;
+  if (!preprocessFrame(d, frame, width, height, &im, &err)) return fail(-1, err);
+  memcpy(out, im.Image.data(), sizeof(uint16_t) * (size_t)Np * Np);
+  if (bg_val) *bg_val = im.bg_val;
+  return 0;
+}
+
+extern "C" int fpmhost_tile_grid(int width, int height, int Np, int overlap, int* nx, int* ny) {
+  if (!nx || !ny || Np <= 0 || overlap < 0 || overlap >= Np || width < Np || height < Np) return fail(-1, "bad argument");
+  tileGrid(width, height, Np, overlap, nx, ny);
+  return 0;
+}
+
 extern "C" int fpmhost_device_from_env(void) { return deviceFromEnv(); }

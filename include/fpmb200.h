@@ -98,8 +98,32 @@ int fpmb200_download_objcrop(fpmb200_ctx* ctx, int tile_first, int n, float* obj
 /* Device pointer of tile `tile`'s buffer for zero-copy hand-off (e.g. the final NCCL gather of a
  * multi-GPU run): which = 0 centred spectrum [Nlarge][Nlarge][2] float, 1 objCrop, 2 pupil,
  * 3 intensity stack as the kernel keeps it (float 1/I in the permuted layout of csrc/fpm_update.cuh
- * `stack_offset`).  Consecutive tiles are contiguous. */
+ * `stack_offset`; natural order on the general path), 4 the uint16 stack as uploaded / ingested
+ * ([n_leds][Np][Np]).  Consecutive tiles are contiguous. */
 int fpmb200_device_buffer(fpmb200_ctx* ctx, int which, int tile, void** ptr, unsigned long long* bytes_per_tile);
+
+/* ---- full field of view (the callers either side of the loop; the reference runs one tile per process) ----
+ *
+ * Frame ingest = fpmMain.cpp:109-144 for every tile at once: the camera frame of one LED is copied to the device
+ * once, each tile's Np x Np ROI (origin set below = the reference's cropX/cropY of that tile) is cut, divided by
+ * `divisor` when it is != 1 (darkfieldExpMultiplier of a dark-field LED; cv::divide: round half to even, x/0 = 0,
+ * :128-129), and the frame's background value -- cv::mean of the two Np x Np ROIs at (bk1x,bk1y), (bk2x,bk2y),
+ * averaged, clamped at bg_threshold, rounded (:131-140) -- is subtracted with saturation (:143-144).  The result
+ * becomes LED slot `led_slot` of every tile's stack (the caller passes frames in update order, as for
+ * fpmb200_upload_stack).  `frame` is a host pointer ([height][width] uint16; pinned for an asynchronous copy). */
+int fpmb200_set_tile_origins(fpmb200_ctx* ctx, const int32_t* roi_x, const int32_t* roi_y, int n_tiles);
+int fpmb200_ingest_frame(fpmb200_ctx* ctx, int led_slot, const uint16_t* frame, int width, int height, int divisor,
+                         int bk1x, int bk1y, int bk2x, int bk2y, int bg_threshold, void* stream);
+/* `FPMimg::bg_val` (fpmMain.h:26) of every ingested LED slot, [n_leds]; synchronises. */
+int fpmb200_ingest_bg(fpmb200_ctx* ctx, int32_t* bg_val);
+
+/* Amplitude mosaic of a regular nx x ny grid of tiles (tile index = iy*nx + ix, ROI origin = (x0 + ix*step,
+ * y0 + iy*step), step <= Np): out[Hm][Wm] float with Wm = ((nx-1)*step + Np) * Nlarge/Np, Hm likewise; overlapping
+ * tiles are cross-faded with separable linear ramps.  `tiles_device` = device pointer to nx*ny objCrop images
+ * ([Nlarge][Nlarge][2] float each, e.g. the gathered result of several GPUs) or NULL for this context's own
+ * tiles after fpmb200_finalize.  `out` is a device pointer if out_on_device, else host memory (async on `stream`). */
+int fpmb200_mosaic(fpmb200_ctx* ctx, const void* tiles_device, int nx, int ny, int step, float* out, int out_on_device,
+                   void* stream);
 
 int fpmb200_sync(fpmb200_ctx* ctx);
 

@@ -51,6 +51,14 @@ int  fpmhost_get_image(const fpmhost_dataset* ds, int led_num, uint16_t* out);
 const char* fpmhost_geometry_source(const fpmhost_dataset* ds);
 /* pupilSupport real plane (fpmMain.cpp:304-313), DC-at-corner. */
 int  fpmhost_pupil_support(int Np, int radius, float* mask);
+/* The per-frame preprocessing of loadFPMDataset (fpmMain.cpp:124-144) on one [height][width] uint16 frame: ROI cut at
+ * (cropX,cropY), cv::divide by `divisor` when it is != 1, background estimate from the two ROIs clamped at
+ * bgThreshold, saturating subtraction.  out = [Np][Np]; *bg_val = FPMimg::bg_val. */
+int  fpmhost_preprocess_frame(const uint16_t* frame, int width, int height, int Np, int cropX, int cropY, int bk1x,
+                              int bk1y, int bk2x, int bk2y, int divisor, int bgThreshold, uint16_t* out, int* bg_val);
+/* Regular tile grid over a width x height frame: tile (ix,iy) has its ROI at (ix*(Np-overlap), iy*(Np-overlap));
+ * returns the counts (the reference has one cropX/cropY per run, fpmMain.cpp:532-533). */
+int  fpmhost_tile_grid(int width, int height, int Np, int overlap, int* nx, int* ny);
 /* CUDA ordinal encoded in OPENCV_OPENCL_DEVICE (use_gpu.sh), -1 for CPU:* (use_cpu.sh). */
 int  fpmhost_device_from_env(void);
 

@@ -358,3 +358,27 @@ def rel_l2(a, b) -> float:
     a = np.asarray(a)
     b = np.asarray(b)
     return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def mosaic(obj_crops, nx, ny, step, Np):
+    """Feathered amplitude mosaic of a regular nx x ny grid of tiles (test oracle of fpmb200_mosaic; the reference
+    has no tile loop, fpmMain.cpp:519,532-533).  obj_crops: [nx*ny][L][L] complex; tile (ix,iy) sits at hi-res
+    offset (ix*step*f, iy*step*f), f = L/Np; overlaps are cross-faded with separable ramps
+    w(u) = min(d+1, ov+1)/(ov+1), d = distance to the nearer tile edge, ov = hi-res overlap."""
+    L = obj_crops[0].shape[0]
+    f = L // Np
+    sh = step * f
+    ov = L - sh
+    u = np.arange(L)
+    d = np.minimum(u, L - 1 - u)
+    w1 = np.ones(L) if ov <= 0 else np.where(d >= ov, 1.0, (d + 1.0) / (ov + 1.0))
+    w2 = np.outer(w1, w1)
+    Hm, Wm = (ny - 1) * sh + L, (nx - 1) * sh + L
+    acc = np.zeros((Hm, Wm))
+    ws = np.zeros((Hm, Wm))
+    for iy in range(ny):
+        for ix in range(nx):
+            a = np.abs(np.asarray(obj_crops[iy * nx + ix], dtype=np.complex128))
+            acc[iy * sh:iy * sh + L, ix * sh:ix * sh + L] += w2 * a
+            ws[iy * sh:iy * sh + L, ix * sh:ix * sh + L] += w2
+    return acc / ws

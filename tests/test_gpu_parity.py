@@ -189,6 +189,69 @@ def test_general_path_many_tiles():
     a.close(), b.close()
 
 
+# ---- full field of view: device-side frame ingest and mosaic ---------------------
+@pytest.mark.parametrize("name", ["cfg1_mono_np64", "cfg7_mono_np90"])
+def test_frame_ingest_matches_host_loader(name):
+    """fpmb200_ingest_frame == loadFPMDataset's per-tile preprocessing (fpmMain.cpp:124-144), bit for bit, for every
+    tile and LED: ROI cut, cv::divide for dark-field LEDs, background estimate / clamp / saturating subtract; and the
+    1/I stack it writes drives the update kernels to the same bits as fpmb200_upload_stack of the same images."""
+    import fpmhost
+    c = T.Case(name, 21, 10)
+    N, n_leds = c.N, 10
+    rng = np.random.default_rng(5)
+    W, H, ov = 3 * N + 37, 2 * N + 21, N // 4
+    nx, ny, xs, ys = fpmhost.tile_grid(W, H, N, ov)
+    n_tiles = nx * ny
+    assert n_tiles >= 6
+    frames = (rng.integers(0, 3000, (n_leds, H, W)) + (rng.random((n_leds, H, W)) < 0.01) * 60000).astype(np.uint16)
+    frames[3] += 900                                              # background above the clamp
+    bk1, bk2, thr = (W - N - 3, 2), (5, H - N - 1), 2300
+    divisors = [1, 1, 3, 1, 0, 7, 1, 2, 1, 5]
+    a = c.make_ctx(n_tiles=n_tiles)
+    a.set_tile_origins(xs, ys)
+    for k in range(n_leds):
+        a.ingest_frame(k, frames[k], divisors[k], bk1, bk2, thr)
+    bg = a.ingest_bg()
+    ref = np.zeros((n_tiles, n_leds, N, N), np.uint16)
+    for t in range(n_tiles):
+        for k in range(n_leds):
+            ref[t, k], b = fpmhost.preprocess_frame(frames[k], N, (xs[t], ys[t]), bk1, bk2, divisors[k], thr)
+            assert b == bg[k]
+    assert bg[3] == thr and len(set(bg.tolist())) > 2
+    for t in (0, n_tiles // 2, n_tiles - 1):
+        assert np.array_equal(a.raw_stack(t), ref[t])
+    b_ctx = c.make_ctx(n_tiles=n_tiles)
+    for t in range(n_tiles):
+        b_ctx.upload_stack(t, ref[t])
+    for ctx in (a, b_ctx):
+        ctx.init_tiles()
+        ctx.run(2)
+        ctx.finalize()
+    for t in range(n_tiles):
+        for x, y in zip(a.download(t), b_ctx.download(t)):
+            assert np.array_equal(x, y)
+    a.close(), b_ctx.close()
+
+
+@pytest.mark.parametrize("overlap", [0, 16, 24])
+def test_mosaic(overlap):
+    c = T.Case("cfg1_mono_np64", 31, 12)
+    nx, ny, N = 3, 2, c.N
+    ctx = c.make_ctx(n_tiles=nx * ny)
+    rng = np.random.default_rng(overlap)
+    for t in range(nx * ny):                                    # different content per tile
+        ctx.upload_stack(t, (c.stack * rng.uniform(0.5, 1.0)).astype(np.uint16))
+    ctx.init_tiles()
+    ctx.run(1)
+    ctx.finalize()
+    crops = [ctx.download(t)[1] for t in range(nx * ny)]
+    got = ctx.mosaic(nx, ny, N - overlap)
+    ref = orc.mosaic(crops, nx, ny, N - overlap, N)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    ctx.close()
+
+
 # ---- structure / edge cases ----------------------------------------------------------------------
 def test_dense_support_uses_general_path():
     """A support mask covering the whole window: no bbox pruning, pupil kept in global memory at

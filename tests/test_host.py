@@ -236,3 +236,28 @@ def test_no_cpu_fallback_without_gpu():
     r = subprocess.run([exe, os.path.join(T.CONFIGS, "cfg1_mono_np64.json"), "1"], capture_output=True, text=True, env=env,
                        cwd=T.ROOT)
     assert r.returncode == 3 and "no CPU reconstruction path" in r.stdout
+
+
+def test_preprocess_frame_and_tile_grid():
+    """fpmhost_preprocess_frame == the cv2 statement of fpmMain.cpp:124-144 (cv::divide, cv::mean, saturating
+    cv::subtract); fpmhost_tile_grid counts."""
+    import cv2
+    rng = np.random.default_rng(3)
+    H, W, Np = 150, 210, 48
+    for divisor, thr in ((1, 1000), (3, 1000), (7, 40), (0, 1000)):
+        frame = (rng.integers(0, 4000, (H, W)) + rng.integers(0, 2, (H, W)) * 61000).astype(np.uint16)
+        crop, bk1, bk2 = (31, 17), (100, 90), (5, 60)
+        img, bg = fpmhost.preprocess_frame(frame, Np, crop, bk1, bk2, divisor, thr)
+        roi = frame[crop[1]:crop[1] + Np, crop[0]:crop[0] + Np].copy()
+        if divisor != 1:
+            roi = cv2.divide(roi, np.full(roi.shape, divisor, np.uint16) if divisor else np.zeros(roi.shape, np.uint16))
+        m1 = cv2.mean(frame[bk1[1]:bk1[1] + Np, bk1[0]:bk1[0] + Np])[0]
+        m2 = cv2.mean(frame[bk2[1]:bk2[1] + Np, bk2[0]:bk2[0] + Np])[0]
+        b = min((m2 + m1) / 2, thr)
+        bgv = int(np.floor(b + 0.5))
+        ref = cv2.subtract(roi, np.full(roi.shape, bgv, np.uint16))
+        assert bg == bgv and np.array_equal(img, ref), (divisor, thr)
+    nx, ny, xs, ys = fpmhost.tile_grid(2560, 2160, 128, 0)
+    assert (nx, ny) == (20, 16) and xs[21] == 128 and ys[21] == 128
+    nx, ny, xs, ys = fpmhost.tile_grid(2560, 2160, 128, 32)
+    assert (nx, ny) == (26, 22) and xs[-1] + 128 <= 2560 and ys[-1] + 128 <= 2160
