@@ -770,6 +770,31 @@ extern "C" int fpmb200_mosaic(fpmb200_ctx* c, const void* tiles_device, int nx, 
   return FPMB200_OK;
 }
 
+// ---- single-process multi-GPU hand-off: a plain device buffer on this context's GPU and a (peer) copy of finished
+//      objCrop tiles into it -- the "final gather" of a full-FOV run driven by one host thread ----
+extern "C" int fpmb200_device_alloc(fpmb200_ctx* c, unsigned long long bytes, void** ptr) {
+  if (!c || !ptr) return fail(FPMB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMalloc(ptr, bytes));
+  return FPMB200_OK;
+}
+extern "C" int fpmb200_device_free(fpmb200_ctx* c, void* ptr) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaFree(ptr));
+  return FPMB200_OK;
+}
+extern "C" int fpmb200_copy_objcrop_to(fpmb200_ctx* src, int tile_first, int n, fpmb200_ctx* dst, void* dst_ptr, void* stream) {
+  int rc = check_range(src, tile_first, n);
+  if (rc) return rc;
+  if (!dst || !dst_ptr) return fail(FPMB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(src->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : src->stream;
+  const size_t LL = (size_t)src->L * src->L;
+  CK(cudaMemcpyPeerAsync(dst_ptr, dst->device, src->objCrop + LL * tile_first, src->device, sizeof(float2) * LL * n, st));
+  return FPMB200_OK;
+}
+
 extern "C" int fpmb200_sync(fpmb200_ctx* c) {
   if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
   CK(cudaSetDevice(c->device));

@@ -56,6 +56,9 @@ def load():
         "fpmb200_ingest_frame": (i, [vp, i, vp, i, i, i, i, i, i, i, i, vp]),
         "fpmb200_ingest_bg": (i, [vp, vp]),
         "fpmb200_mosaic": (i, [vp, vp, i, i, i, vp, i, vp]),
+        "fpmb200_device_alloc": (i, [vp, C.c_ulonglong, C.POINTER(vp)]),
+        "fpmb200_device_free": (i, [vp, vp]),
+        "fpmb200_copy_objcrop_to": (i, [vp, i, i, vp, vp, vp]),
         "fpmb200_sync": (i, [vp]),
         "fpmb200_kernel_launches": (C.c_longlong, [vp]),
         "fpmb200_variant": (C.c_char_p, [vp]),
@@ -72,7 +75,8 @@ EXPORTS = ["fpmb200_last_error", "fpmb200_abi_version", "fpmb200_create", "fpmb2
            "fpmb200_upload_pupil_support", "fpmb200_upload_stack", "fpmb200_init_tiles", "fpmb200_run",
            "fpmb200_step", "fpmb200_finalize", "fpmb200_upload_state", "fpmb200_download",
            "fpmb200_download_objcrop", "fpmb200_device_buffer", "fpmb200_set_tile_origins", "fpmb200_ingest_frame",
-           "fpmb200_ingest_bg", "fpmb200_mosaic", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
+           "fpmb200_ingest_bg", "fpmb200_mosaic", "fpmb200_device_alloc", "fpmb200_device_free", "fpmb200_copy_objcrop_to",
+           "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
 
 
 class FpmError(RuntimeError):

@@ -53,6 +53,21 @@ int main(int argc, char** argv) {
                    "       The same-host CPU baseline lives in oracle/ (python bench.py --impl reference)." << std::endl;
       return 3;
     }
+    // Full field of view (not in the reference, which reconstructs the one ROI cropX/cropY): FPM_FOV_OVERLAP=<pixels>
+    // tiles the whole frame; FPM_GPUS=0,1,... shards the tiles over several GPUs of the box.
+    if (const char* fov = getenv("FPM_FOV_OVERLAP")) {
+      std::vector<int> devices;
+      if (const char* gl = getenv("FPM_GPUS")) {
+        for (const char* q = gl; *q;) {
+          devices.push_back(atoi(q));
+          while (*q && *q != ',') ++q;
+          if (*q == ',') ++q;
+        }
+      }
+      if (devices.empty()) devices.push_back(mDataset.cudaDevice);
+      const char* out = argc > 3 ? argv[3] : getenv("FPM_OUTPUT_DIR");
+      return runFPMFullFOV(&mDataset, atoi(fov), devices, out ? out : "") > 0 ? 0 : 1;
+    }
     if (loadFPMDataset(&mDataset) > 0) {                                                             // :590-591
       runFPM(&mDataset);
       const char* out = argc > 3 ? argv[3] : getenv("FPM_OUTPUT_DIR");

@@ -95,3 +95,10 @@ void makePupilSupport(int Np, int radius, std::vector<float>* mask);
 // parses OPENCV_OPENCL_DEVICE as exported by use_gpu.sh / use_cpu.sh: returns CUDA ordinal >= 0,
 // -1 for "CPU:*" (not served by this build), 0 when unset.
 int deviceFromEnv();
+
+// Full field of view (host/run_fov.cpp): every frame of the dataset directory is cut into a regular grid of Np x Np
+// tiles (`overlap` pixels shared between neighbours), the tiles are sharded over `devices` (CUDA ordinals), and the
+// result is one amplitude mosaic (written to outDir/mosaic_amp.tif when outDir is not empty).  Returns 1 or -1 like
+// loadFPMDataset.
+int runFPMFullFOV(FPM_Dataset* dataset, int overlap, const std::vector<int>& devices, const std::string& outDir);
+

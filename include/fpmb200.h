@@ -125,6 +125,13 @@ int fpmb200_ingest_bg(fpmb200_ctx* ctx, int32_t* bg_val);
 int fpmb200_mosaic(fpmb200_ctx* ctx, const void* tiles_device, int nx, int ny, int step, float* out, int out_on_device,
                    void* stream);
 
+/* Final gather of a single-process multi-GPU run: a device buffer on `ctx`'s GPU, and an asynchronous (peer) copy of
+ * the objCrop of tiles [tile_first, tile_first+n) of `src` into `dst_ptr` on `dst`'s GPU (ordered on `src`'s
+ * stream, or `stream`).  The multi-process variant is an NCCL send/recv from fpmb200_device_buffer (bench.py). */
+int fpmb200_device_alloc(fpmb200_ctx* ctx, unsigned long long bytes, void** ptr);
+int fpmb200_device_free(fpmb200_ctx* ctx, void* ptr);
+int fpmb200_copy_objcrop_to(fpmb200_ctx* src, int tile_first, int n, fpmb200_ctx* dst, void* dst_ptr, void* stream);
+
 int fpmb200_sync(fpmb200_ctx* ctx);
 
 /* Introspection: kernels launched by this context so far, and the name/shape of the update

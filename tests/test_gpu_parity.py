@@ -417,3 +417,62 @@ def test_fpmMain_end_to_end(tmp_path):
     amp = np.frombuffer(data[8:8 + 4 * c.L * c.L], np.float32).reshape(c.L, c.L)
     st = c.oracle_run(3)
     assert orc.rel_l2(amp, np.abs(orc.obj_crop(st))) < FULL_TOL
+
+
+@pytest.mark.parametrize("gpus", ["", "0,1"])
+def test_fpmMain_full_fov(tmp_path, gpus):
+    """FPM_FOV_OVERLAP: the whole frame tiled, every frame read once and cut on the device, mosaic written; checked
+    against per-tile oracle runs on the host loader's preprocessing of the same frames.  FPM_GPUS=0,1 shards the tiles
+    over two GPUs of the box (final peer-copy gather on the first)."""
+    if gpus:
+        import torch
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs 2 GPUs")
+    import json
+    import fpmhost
+    import synth
+    from test_host import write_tiff16
+    c = T.Case("cfg1_mono_np64", 9, 12)
+    N, L, nx, ny, ov = c.N, c.L, 3, 2, 16
+    step = N - ov
+    W, H = (nx - 1) * step + N + 9, (ny - 1) * step + N + 5
+    j = json.load(open(os.path.join(T.GOLD, "cfg1_mono_np64.embedded.json")))
+    root = tmp_path / "frames"
+    root.mkdir()
+    bk1, bk2 = (W - N, 0), (0, H - N)
+    j.update(datasetRoot=str(root) + "/", cropX=0, cropY=0, bk1cropX=bk1[0], bk1cropY=bk1[1], bk2cropX=bk2[0], bk2cropY=bk2[1],
+             bgThresh=120)
+    (tmp_path / "d.json").write_text(json.dumps(j))
+    # one big synthetic object: a low-res frame per LED = a wide stack cut from independent tiles' forward models
+    frames = np.zeros((len(c.order), H, W), np.uint16)
+    for t in range(6):
+        st = synth.synth_stack(N, L, c.r, c.cx, c.cy, 50 + t)
+        x0, y0 = (t % 3) * 70, (t // 3) * 60
+        for k in range(len(c.order)):
+            h, w = min(N, H - y0), min(N, W - x0)
+            frames[k, y0:y0 + h, x0:x0 + w] = st[k][:h, :w] // 2
+    frames += 100
+    for k, n in enumerate(c.order):
+        write_tiff16(str(root / ("iLED_%04d.tif" % n)), frames[k])
+    out = tmp_path / "out"
+    out.mkdir()
+    exe = os.path.join(T.ROOT, "fpm-opencv_b200", "bin", "fpmMain")
+    env = dict(os.environ, OPENCV_OPENCL_DEVICE="GPU:0", FPM_FOV_OVERLAP=str(ov))
+    if gpus:
+        env["FPM_GPUS"] = gpus
+    r = subprocess.run([exe, str(tmp_path / "d.json"), "2", str(out)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Full FOV: %dx%d frame -> 3x2 tiles of 64 (overlap 16), 12 LEDs, %d GPU(s)" % (W, H, 2 if gpus else 1) in r.stdout
+    assert r.stdout.count("Loaded: iLED_") == 12 and "Iteration 2 Completed (Time:" in r.stdout
+    f = L // N
+    Wm, Hm = ((nx - 1) * step + N) * f, ((ny - 1) * step + N) * f
+    data = open(out / "mosaic_amp.tif", "rb").read()
+    got = np.frombuffer(data[8:8 + 4 * Wm * Hm], np.float32).reshape(Hm, Wm)
+    crops = []
+    for t in range(nx * ny):
+        ox, oy = (t % nx) * step, (t // nx) * step
+        stack = np.stack([fpmhost.preprocess_frame(frames[k], N, (ox, oy), bk1, bk2, 1, 120)[0] for k in range(len(c.order))])
+        st = orc.run(stack, c.cx, c.cy, L, c.r, c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 2, 1)
+        crops.append(orc.obj_crop(st))
+    ref = orc.mosaic(crops, nx, ny, step, N)
+    assert orc.rel_l2(got, ref) < FULL_TOL
