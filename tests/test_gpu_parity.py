@@ -375,7 +375,9 @@ def test_argument_errors_are_reported_not_masked():
     import fpmb200
     ctx = fpmb200.Context(0)
     with pytest.raises(fpmb200.FpmError):
-        ctx.tiles_alloc(1, 100, 400, 10)            # unsupported tile edge
+        ctx.tiles_alloc(1, 98, 392, 10)             # 98 = 2 * 7^2: prime factor 7 in the tile edge
+    with pytest.raises(fpmb200.FpmError):
+        ctx.tiles_alloc(1, 75, 300, 10)             # odd tile edge
     with pytest.raises(fpmb200.FpmError):
         ctx.tiles_alloc(1, 64, 448, 10)             # 448 = 2^6 * 7: prime factor 7
     ctx.tiles_alloc(1, 64, 256, 4)
