@@ -269,7 +269,7 @@ extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
 }
 
 template <int N, int C>
-static bool cluster_fits(fpmb200_ctx* c, int* cpc_out, int* cs_out, size_t* bytes_out) {
+static bool cluster_fits(fpmb200_ctx* c, int* cpc_out, int* cs_out, size_t* bytes_out, int* max_clusters = nullptr) {
   const int NR = c->yhi - c->ylo + 1, NC = c->xhi - c->xlo + 1;
   const int cpc = (NC + C - 1) / C;
   if (cpc > 32) return false;                                  // one lane per column in the column passes
@@ -290,6 +290,7 @@ static bool cluster_fits(fpmb200_ctx* c, int* cpc_out, int* cs_out, size_t* byte
     int n_clusters = 0;
     if (cudaOccupancyMaxActiveClusters(&n_clusters, k, &cfg) != cudaSuccess || n_clusters < 1) { cudaGetLastError(); continue; }
     *cpc_out = cpc; *cs_out = cs; *bytes_out = lay.total;
+    if (max_clusters) *max_clusters = n_clusters;
     return true;
   }
   return false;
@@ -326,8 +327,13 @@ static int select_variant(fpmb200_ctx* c) {
     // tiles that a quarter of the SMs would idle anyway (single-tile runs: lower latency per update)
     const int want = c->cluster_req ? c->cluster_req : (N == 256 ? 8 : (N == 128 && c->n_tiles * 4 <= c->sm_count) ? 4 : 1);
     bool ok = false;
+    int max_clusters = 0;
     if (N == 256 && want == 8) ok = cluster_fits<256, 8>(c, &c->cpc, &c->cs, &c->smem_bytes);
-    else if (N == 128 && want == 4) ok = cluster_fits<128, 4>(c, &c->cpc, &c->cs, &c->smem_bytes);
+    else if (N == 128 && want == 4) {
+      ok = cluster_fits<128, 4>(c, &c->cpc, &c->cs, &c->smem_bytes, &max_clusters);
+      // the library's own choice only pays when every tile's cluster is resident at once (GPC boundaries strand SMs)
+      if (ok && !c->cluster_req && c->n_tiles > max_clusters) ok = false;
+    }
     else if (N == 128 && want == 2) ok = cluster_fits<128, 2>(c, &c->cpc, &c->cs, &c->smem_bytes);
     else if (want != 1 && c->cluster_req)
       return fail(FPMB200_ERR_ARG, "%d CTAs per tile is not available for Np=%d (256: 8; 128: 2 or 4; any: 1)", want, N);
