@@ -52,7 +52,7 @@ struct UpdateParams {
   const short2* crop;       // [n_leds] (x = cropXStart, y = cropYStart)
   const float2* tw;         // [N] exp(-2*pi*i*n/N)
   float2* field_gmem;       // [n_tiles][N][N+1] scratch when the field does not fit shared memory
-  float2* qbuf;             // [n_tiles][N][N] pupil-increment scratch when it does not fit shared memory
+  float2* qbuf;             // (unused)
   int L, n_leds;
   int tile0;                // first tile of this launch
   int slot_begin, n_updates;
@@ -193,7 +193,6 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
 
   float2* objFc = p.objFc + (size_t)tile * L * L;
   float2* Pg = p.pupil + (size_t)tile * N * N;
-  float2* Qg = p.qbuf + (size_t)tile * N * N;
   const float* __restrict__ stack = p.stack + (size_t)tile * p.n_leds * N * N;
 
   auto Pref = [&](int iw, int jw) -> float2& {
@@ -202,7 +201,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   };
   auto Qref = [&](int iw, int jw) -> float2& {
     if constexpr (Q_SMEM) return Qc[(iw - p.ylo) * NC + (jw - p.xlo)];
-    else return Qg[(iw & (N - 1)) * N + (jw & (N - 1))];
+    // no room for a separate buffer: Q takes the place of Phi' in the field (C2 reads Phi'(i,j) and then writes
+    // Q(i,j) from the same thread; pass E consumes it before the next S1 overwrites the field)
+    else return fld[(iw & (N - 1)) * PITCH + (jw & (N - 1))];
   };
   // Exact maxima of the two cells (cellrow, 2*seg) and (cellrow, 2*seg+1) from memory: one warp, 32 columns.
   // Every lane of a half-warp returns its cell's maximum.
@@ -234,7 +235,6 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     const int gi = (iw & (N - 1)) * N + (jw & (N - 1));
     if constexpr (P_SMEM) Pc[t] = Pg[gi];
     if constexpr (Q_SMEM) { Sc[t] = p.support[gi]; Qc[t] = make_float2(0.f, 0.f); }
-    else Qg[gi] = make_float2(0.f, 0.f);
   }
   for (int it = warp; it < gr * (L >> 5); it += NW) {
     const int cellrow = it / (L >> 5), seg = it % (L >> 5);
@@ -242,6 +242,16 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     if ((lane & 15) == 0) U[cellrow * gc + 2 * seg + (lane >> 4)] = cm;
   }
   for (int t = tid; t < tmr * tmc; t += NT) Tm[t] = 0u;
+  if constexpr (!Q_SMEM) {                           // max|P|^2 of the incoming pupil (later maintained by pass E)
+    float pm2 = 0.f;
+    for (int t = tid; t < NR * NC; t += NT) {
+      const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
+      const float2 v = Pg[(iw & (N - 1)) * N + (jw & (N - 1))];
+      pm2 = fmaxf(pm2, fmaf(v.x, v.x, v.y * v.y));
+    }
+    pm2 = warp_max(pm2);
+    if (lane == 0) red[32 + warp] = pm2;
+  }
   // crop origins of this update, the next and the one after (windows are fetched one update ahead)
   short2 cr_a = p.crop[p.slot_begin % p.n_leds], cr_b = p.crop[(p.slot_begin + 1) % p.n_leds];
   uint32_t wphase = 0;
@@ -290,30 +300,51 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
         const int i0 = g / NC, jc = g - i0 * NC;
         const int jw = p.xlo + jc, j = jw & (N - 1);
         float2 v[R1];
+        if constexpr (Q_SMEM) {
 #pragma unroll
-        for (int m = 0; m < R1; ++m) {
-          const int i = i0 + R2 * m;
-          const int iw = (i < H) ? i : i - N;
-          if (iw >= p.ylo && iw <= p.yhi) {
-            float2 O;
-            if constexpr (Q_SMEM) O = Oc[(iw - p.ylo) * OCP + jc]; else O = wbase[iw * L + jw];
-            const float2 Q = Qref(iw, jw);
-            float2& pr = Pref(iw, jw);
-            float2 Pv = pr;
-            Pv.x = fmaf(Q.x, inv_objf_max, Pv.x);
-            Pv.y = fmaf(Q.y, inv_objf_max, Pv.y);
-            pr = Pv;
-            pm2 = fmaxf(pm2, fmaf(Pv.x, Pv.x, Pv.y * Pv.y));
-            v[m] = cmul(O, Pv);
-          } else v[m] = make_float2(0.f, 0.f);
+          for (int m = 0; m < R1; ++m) {
+            const int i = i0 + R2 * m;
+            const int iw = (i < H) ? i : i - N;
+            if (iw >= p.ylo && iw <= p.yhi) {
+              const float2 O = Oc[(iw - p.ylo) * OCP + jc];
+              const float2 Q = Qref(iw, jw);
+              float2& pr = Pref(iw, jw);
+              float2 Pv = pr;
+              Pv.x = fmaf(Q.x, inv_objf_max, Pv.x);
+              Pv.y = fmaf(Q.y, inv_objf_max, Pv.y);
+              pr = Pv;
+              pm2 = fmaxf(pm2, fmaf(Pv.x, Pv.x, Pv.y * Pv.y));
+              v[m] = cmul(O, Pv);
+            } else v[m] = make_float2(0.f, 0.f);
+          }
+        } else {
+          // window in global memory (the pupil update ran as its own pass E): every load of the work item is issued
+          // before the first use -- one exposed L2 latency per item instead of one per element
+#pragma unroll
+          for (int m = 0; m < R1; ++m) {
+            const int i = i0 + R2 * m;
+            const int iw = (i < H) ? i : i - N;
+            const int iwc = min(max(iw, p.ylo), p.yhi);
+            v[m] = wbase[iwc * L + jw];
+          }
+#pragma unroll
+          for (int m = 0; m < R1; ++m) {
+            const int i = i0 + R2 * m;
+            const int iw = (i < H) ? i : i - N;
+            const bool in = (iw >= p.ylo && iw <= p.yhi);
+            const float2 phi = cmul(v[m], Pref(min(max(iw, p.ylo), p.yhi), jw));
+            v[m] = in ? phi : make_float2(0.f, 0.f);
+          }
         }
         fftR<R1, true>(v);
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1)
           fld[(i0 + R2 * k1) * PITCH + j] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
       }
-      pm2 = warp_max(pm2);
-      if (lane == 0) red[32 + warp] = pm2;
+      if constexpr (Q_SMEM) {
+        pm2 = warp_max(pm2);
+        if (lane == 0) red[32 + warp] = pm2;
+      }
     }
     __syncthreads();
     FPM_TICK(1);
@@ -484,9 +515,20 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       const float inv_pmax = rsqrt_fast(pm2);                                  // 1 / max|P|
       const int n = NR * NC;
       int ir = tid / NC, jc = tid - ir * NC;
-      for (int base = 0; base < n; base += 2 * NT) {
+      constexpr int CU = Q_SMEM ? 2 : 6;                                       // elements in flight per thread
+      for (int base = 0; base < n; base += CU * NT) {
+        float2 Og[Q_SMEM ? 1 : CU];
+        if constexpr (!Q_SMEM) {                                               // window in global memory: loads first
+          int ir2 = ir, jc2 = jc;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+          for (int k = 0; k < CU; ++k) {
+            Og[k] = (base + k * NT + tid < n) ? wbase[(p.ylo + ir2) * L + p.xlo + jc2] : make_float2(0.f, 0.f);
+            ir2 += qNT; jc2 += rNT;
+            if (jc2 >= NC) { jc2 -= NC; ++ir2; }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < CU; ++k) {
           const int t = base + k * NT + tid;
           if (t < n) {
             const int iw = p.ylo + ir, jw = p.xlo + jc;
@@ -495,7 +537,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
             if constexpr (Q_SMEM) sup = Sc[t]; else sup = __ldg(p.support + i * N + j);
             float2* gp = wbase + iw * L + jw;
             float2 O;
-            if constexpr (Q_SMEM) O = Oc[ir * OCP + jc]; else O = *gp;
+            if constexpr (Q_SMEM) O = Oc[ir * OCP + jc]; else O = Og[k];
             const float2 Pv = Pref(iw, jw);
             const float2 d = csub(fld[i * PITCH + j], cmul(O, Pv));           // dPhi = Phi' - Phi
             // dO = d * |P| conj(P) / (max|P| * ((|P|^2 + delta2) + i*kappa*delta2))
@@ -535,14 +577,38 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
         for (int it = warp + EPRE * NW; it < NR; it += NW)
           if (evalid) { const float2 o = __ldcg(objFc + (size_t)(r0 + it) * L + wc0 + ecw); W[(it << wsh) + ecw] = fmaf(o.x, o.x, o.y * o.y); }
       } else {
-        for (int t = tid; t < n_out; t += NT) {                                  // large rectangles / multi-row cells
-          const int rr = t >> wsh, cw = t - (rr << wsh), r = rt0 + rr, c = wc0 + cw;
-          if (cw < wcols && (r < r0 || r > r1 || c < c0 || c > c1)) {
-            const float2 o = __ldcg(objFc + (size_t)r * L + c);
-            const float a2o = fmaf(o.x, o.x, o.y * o.y);
-            if constexpr (Q_SMEM) W[t] = a2o;
-            else atomicMax(&Tm[(rr >> p.cs) * tmc + (cw >> 4)], __float_as_uint(a2o));
+        // large rectangles / multi-row cells: the frame of the touched cells around the rectangle, as four strips
+        // (above, below: full width; left, right: rectangle rows), four loads in flight per thread
+        (void)n_out;
+        const int rt1 = rt0 + nrt - 1;
+        const int n_top = (r0 - rt0) * wcols, n_bot = (rt1 - r1) * wcols;
+        const int wl = c0 - wc0, wrt = wc0 + wcols - 1 - c1;
+        const int n_all = n_top + n_bot + NR * (wl + wrt);
+        constexpr int DU = 4;
+        for (int base = tid; base < n_all; base += DU * NT) {
+          float2 o[DU];
+          int rr[DU], cw[DU];
+#pragma unroll
+          for (int k = 0; k < DU; ++k) {
+            const int t = base + k * NT;
+            rr[k] = -1;
+            if (t < n_all) {
+              int r, c;
+              if (t < n_top) { r = rt0 + t / wcols; c = wc0 + t % wcols; }
+              else if (t < n_top + n_bot) { const int q = t - n_top; r = r1 + 1 + q / wcols; c = wc0 + q % wcols; }
+              else if (t < n_top + n_bot + NR * wl) { const int q = t - n_top - n_bot; r = r0 + q / wl; c = wc0 + q % wl; }
+              else { const int q = t - n_top - n_bot - NR * wl; r = r0 + q / wrt; c = c1 + 1 + q % wrt; }
+              o[k] = __ldcg(objFc + (size_t)r * L + c);
+              rr[k] = r - rt0; cw[k] = c - wc0;
+            }
           }
+#pragma unroll
+          for (int k = 0; k < DU; ++k)
+            if (rr[k] >= 0) {
+              const float a2o = fmaf(o[k].x, o[k].x, o[k].y * o[k].y);
+              if constexpr (Q_SMEM) W[(rr[k] << wsh) + cw[k]] = a2o;
+              else atomicMax(&Tm[(rr[k] >> p.cs) * tmc + (cw[k] >> 4)], __float_as_uint(a2o));
+            }
         }
       }
     }
@@ -592,6 +658,40 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       for (int w = 1; w < NW; ++w) om2 = fmaxf(om2, red[w]);
       inv_objf_max = rsqrt_fast(om2);                // applied to P by the next S1 (or by the epilogue below)
     }
+    if constexpr (!Q_SMEM) {
+      // ===== E: pupil update P += Q / max|objF| (fpmMain.cpp:470-475) as its own coalesced pass; max|P|^2 =====
+      float pm2 = 0.f;
+      constexpr int EU = 5;                          // Q loads in flight per thread
+      int ir = tid / NC, jc = tid - ir * NC;
+      for (int base = tid; base < NR * NC; base += EU * NT) {
+        float2 Qv[EU];
+        {
+          int ir2 = ir, jc2 = jc;
+#pragma unroll
+          for (int k = 0; k < EU; ++k) {
+            Qv[k] = (base + k * NT < NR * NC) ? Qref(p.ylo + ir2, p.xlo + jc2) : make_float2(0.f, 0.f);
+            ir2 += qNT; jc2 += rNT;
+            if (jc2 >= NC) { jc2 -= NC; ++ir2; }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < EU; ++k) {
+          if (base + k * NT < NR * NC) {
+            float2& pr = Pref(p.ylo + ir, p.xlo + jc);
+            float2 v = pr;
+            v.x = fmaf(Qv[k].x, inv_objf_max, v.x);
+            v.y = fmaf(Qv[k].y, inv_objf_max, v.y);
+            pr = v;
+            pm2 = fmaxf(pm2, fmaf(v.x, v.x, v.y * v.y));
+          }
+          ir += qNT; jc += rNT;
+          if (jc >= NC) { jc -= NC; ++ir; }
+        }
+      }
+      pm2 = warp_max(pm2);
+      if (lane == 0) red[32 + warp] = pm2;          // read by the next update's C2, several barriers from here
+      __syncthreads();                               // P is complete before the next S1 reads it
+    }
     cr_a = cr_b; cr_b = cr_c;
     FPM_TICK(10);
   }
@@ -603,15 +703,16 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   }
 #endif
   if constexpr (Q_SMEM) { if (tid == 0) tma_store_wait_all(); }   // the last window stores have read their buffers
-  // the last update's pupil increment is still pending
-  for (int t = tid; t < NR * NC; t += NT) {
-    const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
-    const float2 Q = Qref(iw, jw);
-    float2& pr = Pref(iw, jw);
-    float2 v = pr;
-    v.x = fmaf(Q.x, inv_objf_max, v.x);
-    v.y = fmaf(Q.y, inv_objf_max, v.y);
-    pr = v;
+  if constexpr (Q_SMEM) {                           // the last update's pupil increment is still pending
+    for (int t = tid; t < NR * NC; t += NT) {
+      const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
+      const float2 Q = Qref(iw, jw);
+      float2& pr = Pref(iw, jw);
+      float2 v = pr;
+      v.x = fmaf(Q.x, inv_objf_max, v.x);
+      v.y = fmaf(Q.y, inv_objf_max, v.y);
+      pr = v;
+    }
   }
   __syncthreads();
   if constexpr (P_SMEM) {

@@ -49,7 +49,7 @@ struct fpmb200_ctx {
   float2* twN = nullptr;       // [N]
   float2* twL = nullptr;       // [L]
   float2* field_gmem = nullptr;
-  float2* qbuf = nullptr;      // [n_tiles][N][N] when the pupil increment does not fit shared memory
+  float2* qbuf = nullptr;      // (unused: the pupil increment lives in the field buffer when it has no buffer of its own)
   float2* scratch = nullptr;   // staging: max(L*L, init batch * N*N)
   size_t scratch_elems = 0;
   int ylo = 0, yhi = -1, xlo = 0, xhi = -1;
@@ -364,11 +364,6 @@ static int select_variant(fpmb200_ctx* c) {
   c->smem_bytes = update_smem_bytes(c, c->field_smem, c->p_smem, c->q_smem, cs);
   if (!c->field_smem && !c->field_gmem)
     CK(cudaMalloc(&c->field_gmem, sizeof(float2) * (size_t)N * (N + 1) * c->n_tiles));
-  if (!c->q_smem && !c->qbuf) {
-    CK(cudaMalloc(&c->qbuf, sizeof(float2) * (size_t)N * N * c->n_tiles));
-    CK(cudaMemsetAsync(c->qbuf, 0, sizeof(float2) * (size_t)N * N * c->n_tiles, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
   c->ocp = ((xhi - xlo + 1) + 2) & ~1;       // even, with room for the 16-byte alignment of TMA box starts
   c->have_tmap = false;
   if (c->q_smem) {
@@ -391,7 +386,7 @@ static int select_variant(fpmb200_ctx* c) {
   }
   snprintf(c->variant, sizeof c->variant,
            "fpm_update_kernel<N=%d,field=%s,pupil=%s,dP=%s> bbox=[%d..%d]x[%d..%d] maxcell=%dx16 smem=%zuB", N,
-           c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", c->q_smem ? "smem" : "gmem", ylo, yhi, xlo, xhi,
+           c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", c->q_smem ? "smem" : "field", ylo, yhi, xlo, xhi,
            1 << cs, c->smem_bytes);
   return FPMB200_OK;
 }
