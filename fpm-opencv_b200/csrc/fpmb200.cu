@@ -576,7 +576,7 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
     return fail(FPMB200_ERR_STATE, "no cluster kernel for Np=%d x %d CTAs", c->N, c->cluster);
   }
   switch (c->N) {
-    case 64: return launch_update<64, 256, 2>(c, p, n, st);
+    case 64: return launch_update<64, 512, 1>(c, p, n, st);
     case 128: return launch_update<128, 512, 1>(c, p, n, st);
     case 256: return launch_update<256, 512, 1>(c, p, n, st);
   }
