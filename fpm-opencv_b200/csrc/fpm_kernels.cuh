@@ -33,7 +33,7 @@ struct LineFFTParams {
 };
 
 template <bool INV, int LINES>
-__global__ void __launch_bounds__(256) line_fft_kernel(const LineFFTParams p) {
+__global__ void __launch_bounds__(256) line_fft_kernel(const __grid_constant__ LineFFTParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* bufA = reinterpret_cast<float2*>(smem_raw);
   float2* bufB = bufA + (size_t)LINES * p.n;

@@ -284,8 +284,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
     const int nslot2 = (nslot + 1 == p.n_leds) ? 0 : nslot + 1;
     const short2 cr_c = p.crop[nslot2];
-    float2* Oc = Ocb[u & 1] + ((xs + H + p.xlo) & 1);              // window element (ir, jc) = Oc[ir*OCP + jc]
-    float2* Ocn = Ocb[(u & 1) ^ 1];                                // next window's box, box-relative columns
+    float2* const Ocur = (u & 1) ? Ocb[1] : Ocb[0];                // (selects, not a runtime-indexed local array)
+    float2* Oc = Ocur + ((xs + H + p.xlo) & 1);                    // window element (ir, jc) = Oc[ir*OCP + jc]
+    float2* Ocn = (u & 1) ? Ocb[0] : Ocb[1];                       // next window's box, box-relative columns
     if constexpr (Q_SMEM) { if (u == 0) { mbar_wait(&wbar, wphase); wphase ^= 1; } }
     const float* __restrict__ img = stack + (size_t)slot * N * N;
     if (tid == 0)   // pull the next LED's intensity tile towards L2 while this update runs
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     __syncthreads();
     FPM_TICK(8);
     if constexpr (Q_SMEM) {
-      if (tid == 0) tma_store_window(Ocb[u & 1], &p.tmap, 2 * (c0 & ~1), r0, tile);   // updated window -> objFc
+      if (tid == 0) tma_store_window(Ocur, &p.tmap, 2 * (c0 & ~1), r0, tile);          // updated window -> objFc
     }
     // ===== D: the touched cells take their rebuilt maxima; max|objF|^2 = max over the whole grid =====
     for (int t = tid; t < ncr * ncc; t += NT) {          // one thread per touched cell
