@@ -71,6 +71,9 @@ struct fpmb200_ctx {
   float* gcells = nullptr;     // [n_tiles][cgr][cgc]
   float* gscal = nullptr;      // [n_tiles][4]
   int cgr = 0, cgc = 0;
+  // one pass over all LEDs of the general path (11 launches per LED) captured as a CUDA graph, per tile range
+  struct IterGraph { int first, n; cudaGraphExec_t exec; long long nodes; };
+  std::vector<IterGraph> iter_graphs;
   // full-FOV helpers (csrc/fpm_fov.cuh)
   int2* origins = nullptr;     // [n_tiles] ROI origin of every tile in the camera frame
   bool have_origins = false;
@@ -122,7 +125,10 @@ static cudaError_t copy_sync(fpmb200_ctx* c, void* dst, const void* src, size_t 
   return cudaStreamSynchronize(c->stream);
 }
 
+static void drop_graphs(fpmb200_ctx* c);
+
 static void free_tiles(fpmb200_ctx* c) {
+  drop_graphs(c);
   cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->raw); cudaFree(c->support);
   cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch); cudaFree(c->qbuf);
   cudaFree(c->gfield); cudaFree(c->gq); cudaFree(c->gcells); cudaFree(c->gscal);
@@ -199,6 +205,7 @@ extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlar
 extern "C" int fpmb200_set_params(fpmb200_ctx* c, float delta1, float delta2, float eps, int literal_scalar) {
   if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
   c->delta1 = delta1; c->delta2 = delta2; c->eps = eps; c->kappa = literal_scalar ? 1.f : 0.f;
+  drop_graphs(c);
   return FPMB200_OK;
 }
 
@@ -515,6 +522,11 @@ static int fft2d(fpmb200_ctx* c, float2* data, int n, const float2* tw, int batc
                  cudaStream_t st);
 
 // The unfused path (csrc/fpm_general.cuh): 11 launches per update, every launch covers tiles [first, first+n).
+static void drop_graphs(fpmb200_ctx* c) {
+  for (auto& g : c->iter_graphs) cudaGraphExecDestroy(g.exec);
+  c->iter_graphs.clear();
+}
+
 static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
   GeneralParams p;
   memset(&p, 0, sizeof p);
@@ -535,19 +547,50 @@ static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin,
   gen_pupil_update<<<ge, 256, 0, st>>>(p);
   c->launches += 3;
   p.apply = 1;
+  auto enqueue = [&](int u0, int u1) -> int {
+    int rc;
+    for (int u = u0; u < u1; ++u) {
+      p.slot = (slot_begin + u) % c->n_leds;
+      gen_window_mul<<<ge, 256, 0, st>>>(p);
+      if ((rc = fft2d<true>(c, fld, N, c->twN, n, (long long)N * N, 1.f / ((float)N * (float)N), st))) return rc;
+      gen_amplitude<<<ge, 256, 0, st>>>(p);
+      if ((rc = fft2d<false>(c, fld, N, c->twN, n, (long long)N * N, 1.f, st))) return rc;
+      gen_object_update<<<ge, 256, 0, st>>>(p);
+      gen_cells_update<<<dim3(tc * tc, n), 256, 0, st>>>(p, 0);
+      gen_cells_max<<<n, 256, 0, st>>>(p);
+      gen_pupil_update<<<ge, 256, 0, st>>>(p);
+      c->launches += 10;
+    }
+    return FPMB200_OK;
+  };
   int rc;
-  for (int u = 0; u < n_updates; ++u) {
-    p.slot = (slot_begin + u) % c->n_leds;
-    gen_window_mul<<<ge, 256, 0, st>>>(p);
-    if ((rc = fft2d<true>(c, fld, N, c->twN, n, (long long)N * N, 1.f / ((float)N * (float)N), st))) return rc;
-    gen_amplitude<<<ge, 256, 0, st>>>(p);
-    if ((rc = fft2d<false>(c, fld, N, c->twN, n, (long long)N * N, 1.f, st))) return rc;
-    gen_object_update<<<ge, 256, 0, st>>>(p);
-    gen_cells_update<<<dim3(tc * tc, n), 256, 0, st>>>(p, 0);
-    gen_cells_max<<<n, 256, 0, st>>>(p);
-    gen_pupil_update<<<ge, 256, 0, st>>>(p);
-    c->launches += 6;
+  // whole passes over the LED list replay a captured graph (the loop is launch-bound for a handful of tiles)
+  const int nl = c->n_leds;
+  if (slot_begin == 0 && n_updates >= nl && n_updates % nl == 0) {
+    fpmb200_ctx::IterGraph* g = nullptr;
+    for (auto& e : c->iter_graphs) if (e.first == first && e.n == n) g = &e;
+    if (!g) {
+      const long long l0 = c->launches;
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      rc = enqueue(0, nl);
+      cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      CK(e2);
+      cudaGraphExec_t exec = nullptr;
+      CK(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      c->iter_graphs.push_back({first, n, exec, c->launches - l0});
+      c->launches = l0;
+      g = &c->iter_graphs.back();
+    }
+    for (int it = 0; it < n_updates / nl; ++it) {
+      CK(cudaGraphLaunch(g->exec, st));
+      c->launches += g->nodes;
+    }
+    return FPMB200_OK;
   }
+  if ((rc = enqueue(0, n_updates))) return rc;
   CK(cudaGetLastError());
   return FPMB200_OK;
 }
