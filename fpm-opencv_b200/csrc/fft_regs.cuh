@@ -63,6 +63,16 @@ template <bool INV> __host__ __device__ __forceinline__ float2 twmul(float2 a, f
   return INV ? cmulc(a, w) : cmul(a, w);
 }
 
+// a * w from a table entry t = (w.x, s*w.y, -s*w.y, w.x): s = +1 gives a*w, s = -1 gives a*conj(w).  The same two
+// packed operations as cmul / cmulc without the half negation they need for a plain (w.x, w.y) operand.
+__host__ __device__ __forceinline__ float2 twmul4(float2 a, float4 t) {
+#if FPM_PACKED
+  return __ffma2_rn(make_float2(a.x, a.x), make_float2(t.x, t.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(t.z, t.w)));
+#else
+  return make_float2(fmaf(a.x, t.x, a.y * t.z), fmaf(a.x, t.y, a.y * t.w));
+#endif
+}
+
 template <bool INV> __host__ __device__ __forceinline__ void fft2(float2& a, float2& b) {
   float2 t = a;
   a = cadd(t, b);
@@ -144,13 +154,9 @@ template <bool INV, int n> __host__ __device__ __forceinline__ float2 mulW16(flo
   }
 }
 
-template <bool INV> __host__ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
-  // radix-4 DIT: four stride-4 sub-transforms A_j (j = 0..3) ...
-  fft4<INV>(v[0], v[4], v[8], v[12]);
-  fft4<INV>(v[1], v[5], v[9], v[13]);
-  fft4<INV>(v[2], v[6], v[10], v[14]);
-  fft4<INV>(v[3], v[7], v[11], v[15]);
-  // A_j[k] now sits in v[j + 4k]; twiddle by W16^(j*k)
+// second half of the radix-4 x radix-4 DIT 16-point transform: A_j[k] (j = sub-transform, k = its output) sits in
+// v[j + 4k]; twiddle by W16^(j*k), then for every k a 4-point transform over j
+template <bool INV> __host__ __device__ __forceinline__ void fft16_tail(float2 (&v)[16]) {
   v[5] = mulW16<INV, 1>(v[5]);   v[6] = mulW16<INV, 2>(v[6]);    v[7] = mulW16<INV, 3>(v[7]);
   v[9] = mulW16<INV, 2>(v[9]);   v[10] = mulW16<INV, 4>(v[10]);  v[11] = mulW16<INV, 6>(v[11]);
   v[13] = mulW16<INV, 3>(v[13]); v[14] = mulW16<INV, 6>(v[14]);  v[15] = mulW16<INV, 9>(v[15]);
@@ -164,6 +170,36 @@ template <bool INV> __host__ __device__ __forceinline__ void fft16(float2 (&v)[1
 #define FPM_SWAP(a, b) t = v[a]; v[a] = v[b]; v[b] = t;
   FPM_SWAP(1, 4) FPM_SWAP(2, 8) FPM_SWAP(3, 12) FPM_SWAP(6, 9) FPM_SWAP(7, 13) FPM_SWAP(11, 14)
 #undef FPM_SWAP
+}
+
+template <bool INV> __host__ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
+  // radix-4 DIT: four stride-4 sub-transforms A_j (j = 0..3) ...
+  fft4<INV>(v[0], v[4], v[8], v[12]);
+  fft4<INV>(v[1], v[5], v[9], v[13]);
+  fft4<INV>(v[2], v[6], v[10], v[14]);
+  fft4<INV>(v[3], v[7], v[11], v[15]);
+  fft16_tail<INV>(v);
+}
+
+// 16-point transform of an input whose entries 3..12 are zero: w = (x[0], x[1], x[2], x[13], x[14], x[15]).
+// The first radix-4 layer of fft16 degenerates (8 complex additions instead of 32); the result equals fft16 of the
+// zero-padded input bit for bit (x + 0 and 0 - x are exact), up to the sign of exact zeros.
+template <bool INV> __host__ __device__ __forceinline__ void fft16_in6(const float2 (&w)[6], float2 (&v)[16]) {
+  const float2 x0 = w[0], x1 = w[1], x2 = w[2], x13 = w[3], x14 = w[4], x15 = w[5];
+  v[0] = x0; v[4] = x0; v[8] = x0; v[12] = x0;                       // j = 0: (x0, 0, 0, 0)
+  {                                                                  // j = 1: (x1, 0, 0, x13)
+    const float2 r = rot90<INV>(x13);
+    v[1] = cadd(x1, x13); v[5] = csub(x1, r); v[9] = csub(x1, x13); v[13] = cadd(x1, r);
+  }
+  {                                                                  // j = 2: (x2, 0, 0, x14)
+    const float2 r = rot90<INV>(x14);
+    v[2] = cadd(x2, x14); v[6] = csub(x2, r); v[10] = csub(x2, x14); v[14] = cadd(x2, r);
+  }
+  {                                                                  // j = 3: (0, 0, 0, x15)
+    const float2 r = rot90<INV>(x15);
+    v[3] = x15; v[7] = make_float2(-r.x, -r.y); v[11] = make_float2(-x15.x, -x15.y); v[15] = r;
+  }
+  fft16_tail<INV>(v);
 }
 
 // ---- compile-time loop and 32nd roots of unity -------------------------------------------

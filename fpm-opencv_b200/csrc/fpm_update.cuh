@@ -146,10 +146,15 @@ __device__ __forceinline__ void tma_store_window(const void* src, const CUtensor
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int N, int NT, int MINB, bool FIELD_SMEM, bool P_SMEM, bool Q_SMEM>
+// NARROW: the support bbox lies inside [-(3*R2-1), 3*R2-1] in both directions (N = 128: a pupil radius <= 23, the shipped
+// 128-pixel configurations).  Then only 6 of the 16 inputs of every first-stage radix-16 butterfly can be non-zero
+// (S1, S3: fft16_in6) and only 6 of the 16 outputs of every last-stage butterfly are ever read (S5, S7: the others are
+// not stored and their arithmetic is dead code); the set is known at compile time.
+template <int N, int NT, int MINB, bool FIELD_SMEM, bool P_SMEM, bool Q_SMEM, bool NARROW = false>
 __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_constant__ UpdateParams p) {
   using S = Shape<N>;
   constexpr int R1 = S::R1, R2 = S::R2, PITCH = S::PITCH, CH = S::CH;
+  static_assert(!NARROW || (R1 == 16 && P_SMEM && Q_SMEM), "narrow-pupil specialisation");
   constexpr int H = N / 2, NW = NT / 32;
   extern __shared__ __align__(1024) unsigned char smem_raw[];   // TMA destinations need 128-byte alignment
 
@@ -159,6 +164,8 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   const int NR = p.yhi - p.ylo + 1, NC = p.xhi - p.xlo + 1;
   const int gc = L >> 4, gr = L >> p.cs;                 // max-cells are (1<<cs) rows x 16 columns
   const int qNT = NT / NC, rNT = NT % NC;                 // element index stepping: t += NT without dividing
+  const int tq = tid / NC, tr = tid - tq * NC;            // (row, column) of work item tid in every NC-wide decomposition
+  auto step_nt = [&](int& q, int& r) { q += qNT; r += rNT; if (r >= NC) { r -= NC; ++q; } };
   const int tmr = (NR >> p.cs) + 2, tmc = (NC >> 4) + 2;   // cells a bbox rectangle can touch
   const int wshmax = 32 - __clz((tmc << 4) - 1);           // log2 of the padded width of the touched-cell window
 
@@ -167,8 +174,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   float2* fld;
   if constexpr (FIELD_SMEM) { fld = reinterpret_cast<float2*>(sp); sp += (sizeof(float2) * N * PITCH + 15) / 16 * 16; }
   else fld = p.field_gmem + (size_t)tile * N * PITCH;
-  float2* twA = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * N;   // [b*R2 + a] = W^(a*b)
-  float2* twB = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * N;   // [a*R1 + b] = W^(a*b)
+  // twiddles as twmul4 operands: twA (inverse stages) [b*R2 + a] = conj(W^(a*b)), twB (forward stages) [a*R1 + b] = W^(a*b)
+  float4* twA = reinterpret_cast<float4*>(sp); sp += sizeof(float4) * N;
+  float4* twB = reinterpret_cast<float4*>(sp); sp += sizeof(float4) * N;
   float* red = reinterpret_cast<float*>(sp);   sp += sizeof(float) * 64;   // [0..31] objF, [32..63] pupil partial maxima
   float2* Pc = nullptr;
   if constexpr (P_SMEM) { Pc = reinterpret_cast<float2*>(sp); sp += sizeof(float2) * NR * NC; }
@@ -226,9 +234,11 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   // ---- prologue: tables, pupil -> shared memory, max|P|^2, max-cell grid, first window ----
   for (int t = tid; t < N; t += NT) {
     const int b = t / R2, a = t % R2;
-    twA[t] = p.tw[a * b];
+    const float2 wa = p.tw[a * b];
+    twA[t] = make_float4(wa.x, -wa.y, wa.y, wa.x);
     const int a2 = t / R1, b2 = t % R1;
-    twB[t] = p.tw[a2 * b2];
+    const float2 wb = p.tw[a2 * b2];
+    twB[t] = make_float4(wb.x, wb.y, -wb.y, wb.x);
   }
   for (int t = tid; t < NR * NC; t += NT) {
     const int iw = p.ylo + t / NC, jw = p.xlo + t % NC;
@@ -297,11 +307,31 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     //       Phi = O*P and cols stage A (inverse).  max|P|^2 for this update's object step is reduced on the way. =====
     {
       float pm2 = 0.f;
-      for (int g = tid; g < R2 * NC; g += NT) {
-        const int i0 = g / NC, jc = g - i0 * NC;
+      for (int g = tid, i0 = tq, jc = tr; g < R2 * NC; g += NT) {
         const int jw = p.xlo + jc, j = jw & (N - 1);
         float2 v[R1];
-        if constexpr (Q_SMEM) {
+        if constexpr (NARROW) {
+          // inputs i = i0 + R2*m inside the bbox: m = 0, 1, 2 (iw = i) and m = R1-3 .. R1-1 (iw = i - N) at most
+          float2 w6[6];
+          const int ob = (i0 - p.ylo) * OCP + jc, pb = (i0 - p.ylo) * NC + jc;
+          static_for<0, 6>([&](auto K) {
+            constexpr int k = decltype(K)::value;
+            constexpr int off = (k < 3) ? R2 * k : R2 * (R1 - 6 + k) - N;      // iw = i0 + off
+            const int iw = i0 + off;
+            const bool in = (iw >= p.ylo) && (iw <= p.yhi);
+            const int oi = in ? ob + off * OCP : 0, pi = in ? pb + off * NC : 0;
+            const float2 O = Oc[oi], Q = Qc[pi];
+            float2 Pv = Pc[pi];
+            Pv.x = fmaf(Q.x, inv_objf_max, Pv.x);
+            Pv.y = fmaf(Q.y, inv_objf_max, Pv.y);
+            if (in) Pc[pi] = Pv;
+            pm2 = fmaxf(pm2, in ? fmaf(Pv.x, Pv.x, Pv.y * Pv.y) : 0.f);
+            const float2 phi = cmul(O, Pv);
+            w6[k] = in ? phi : make_float2(0.f, 0.f);
+          });
+          FPM_TICK(11);
+          fft16_in6<true>(w6, v);
+        } else if constexpr (Q_SMEM) {
 #pragma unroll
           for (int m = 0; m < R1; ++m) {
             const int i = i0 + R2 * m;
@@ -337,10 +367,11 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
             v[m] = in ? phi : make_float2(0.f, 0.f);
           }
         }
-        fftR<R1, true>(v);
+        if constexpr (!NARROW) { FPM_TICK(11); fftR<R1, true>(v); }
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1)
-          fld[(i0 + R2 * k1) * PITCH + j] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
+          fld[(i0 + R2 * k1) * PITCH + j] = twmul4(v[k1], twA[k1 * R2 + i0]);
+        step_nt(i0, jc);
       }
       if constexpr (Q_SMEM) {
         pm2 = warp_max(pm2);
@@ -350,8 +381,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     __syncthreads();
     FPM_TICK(1);
     // ================= S2: cols stage B (inverse) =================
-    for (int g = tid; g < R1 * NC; g += NT) {
-      const int k1 = g / NC, jc = g - k1 * NC;
+    for (int g = tid, k1 = tq, jc = tr; g < R1 * NC; g += NT) {
       const int js = (p.xlo + jc) & (N - 1);
       float2 v[R2];
 #pragma unroll
@@ -359,6 +389,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       fftR<R2, true>(v);
 #pragma unroll
       for (int a = 0; a < R2; ++a) fld[(R2 * k1 + a) * PITCH + js] = v[a];
+      step_nt(k1, jc);
     }
     __syncthreads();
     FPM_TICK(2);
@@ -377,15 +408,26 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       const int row = g % N, j0 = g / N;
       float2* rp = fld + row * PITCH + j0;
       float2 v[R1];
+      if constexpr (NARROW) {
+        float2 w6[6];
+        static_for<0, 6>([&](auto K) {
+          constexpr int k = decltype(K)::value;
+          constexpr int m = (k < 3) ? k : R1 - 6 + k;
+          const int jw = (k < 3) ? j0 + R2 * m : j0 + R2 * m - N;
+          w6[k] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);     // (j0 is warp-uniform)
+        });
+        fft16_in6<true>(w6, v);
+      } else {
 #pragma unroll
-      for (int m = 0; m < R1; ++m) {
-        const int col = j0 + R2 * m;
-        const int jw = (R2 * m < H) ? col : col - N;                 // R2 | H: the group does not straddle H
-        v[m] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);
+        for (int m = 0; m < R1; ++m) {
+          const int col = j0 + R2 * m;
+          const int jw = (R2 * m < H) ? col : col - N;                 // R2 | H: the group does not straddle H
+          v[m] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);
+        }
+        fftR<R1, true>(v);
       }
-      fftR<R1, true>(v);
 #pragma unroll
-      for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
+      for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul4(v[k1], twA[k1 * R2 + j0]);
     }
     row_block_sync();          // S3 -> S4 -> S5 exchange data only within a block of 32 rows (= NT/N warps)
     FPM_TICK(3);
@@ -432,7 +474,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       }
       fftR<R2, false>(v);
 #pragma unroll
-      for (int q = 0; q < R2; ++q) rp[q] = twmul<false>(v[q], twB[q * R1 + k1]);
+      for (int q = 0; q < R2; ++q) rp[q] = twmul4(v[q], twB[q * R1 + k1]);
     }
     row_block_sync();
     FPM_TICK(4);
@@ -444,38 +486,58 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
 #pragma unroll
       for (int k1 = 0; k1 < R1; ++k1) v[k1] = rp[R2 * k1];
       fftR<R1, false>(v);
+      if constexpr (NARROW) {
+        // S6, S7 and C2 read bbox columns only: six candidate outputs, the rest of the butterfly is dead code
+        static_for<0, 6>([&](auto K) {
+          constexpr int k = decltype(K)::value;
+          constexpr int r = (k < 3) ? k : R1 - 6 + k;
+          const int jw = (k < 3) ? q + R2 * r : q + R2 * r - N;
+          if (jw >= p.xlo && jw <= p.xhi) rp[R2 * r] = v[r];                            // (q is warp-uniform)
+        });
+      } else {
 #pragma unroll
-      for (int r = 0; r < R1; ++r) rp[R2 * r] = v[r];
+        for (int r = 0; r < R1; ++r) rp[R2 * r] = v[r];
+      }
     }
     __syncthreads();
     FPM_TICK(5);
     // ================= S6: cols stage B' (forward) =================
-    for (int g = tid; g < R1 * NC; g += NT) {
-      const int k1 = g / NC, jc = g - k1 * NC;
+    for (int g = tid, k1 = tq, jc = tr; g < R1 * NC; g += NT) {
       const int js = (p.xlo + jc) & (N - 1);
       float2 v[R2];
 #pragma unroll
       for (int a = 0; a < R2; ++a) v[a] = fld[(R2 * k1 + a) * PITCH + js];
       fftR<R2, false>(v);
 #pragma unroll
-      for (int q = 0; q < R2; ++q) fld[(R2 * k1 + q) * PITCH + js] = twmul<false>(v[q], twB[q * R1 + k1]);
+      for (int q = 0; q < R2; ++q) fld[(R2 * k1 + q) * PITCH + js] = twmul4(v[q], twB[q * R1 + k1]);
+      step_nt(k1, jc);
     }
     __syncthreads();
     FPM_TICK(6);
     // ===== S7: cols stage A' (forward) -> Phi' in natural order; only bbox rows are stored (C2 reads nothing else) =====
-    for (int g = tid; g < R2 * NC; g += NT) {
-      const int q = g / NC, jc = g - q * NC;
+    for (int g = tid, q = tq, jc = tr; g < R2 * NC; g += NT) {
       const int js = (p.xlo + jc) & (N - 1);
       float2 v[R1];
 #pragma unroll
       for (int k1 = 0; k1 < R1; ++k1) v[k1] = fld[(R2 * k1 + q) * PITCH + js];
       fftR<R1, false>(v);
+      if constexpr (NARROW) {
+        static_for<0, 6>([&](auto K) {
+          constexpr int k = decltype(K)::value;
+          constexpr int r = (k < 3) ? k : R1 - 6 + k;
+          const int i = R2 * r + q;
+          const int iw = (k < 3) ? i : i - N;
+          if (iw >= p.ylo && iw <= p.yhi) fld[i * PITCH + js] = v[r];
+        });
+      } else {
 #pragma unroll
-      for (int r = 0; r < R1; ++r) {
-        const int i = R2 * r + q;
-        const int iw = (i < H) ? i : i - N;
-        if (iw >= p.ylo && iw <= p.yhi) fld[i * PITCH + js] = v[r];
+        for (int r = 0; r < R1; ++r) {
+          const int i = R2 * r + q;
+          const int iw = (i < H) ? i : i - N;
+          if (iw >= p.ylo && iw <= p.yhi) fld[i * PITCH + js] = v[r];
+        }
       }
+      step_nt(q, jc);
     }
     __syncthreads();
     FPM_TICK(7);
@@ -484,7 +546,9 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     const int cr0 = r0 >> p.cs, ncr = (r1 >> p.cs) - cr0 + 1, cc0 = c0 >> 4, ncc = (c1 >> 4) - cc0 + 1;
     // the next LED's window was fetched by TMA before this update's writes: wait for it, then patch the overlap
     const int r0n = cr_b.y + H + p.ylo, c0n = (cr_b.x + H + p.xlo) & ~1;   // origin of the next window's TMA box
+    FPM_TICK(12);
     if constexpr (Q_SMEM) { if (u > 0) { mbar_wait(&wbar, wphase); wphase ^= 1; } }
+    FPM_TICK(13);
     {
       // Exact max|objF| bookkeeping (fpmMain.cpp:460,467): a grid U of per-cell maxima of |objFc|^2 (2^cs rows x 16
       // columns).  The cells this rectangle touches are rebuilt in Tm by atomicMax: new values of the rectangle's
@@ -501,21 +565,22 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       const bool fast_edges = Q_SMEM && (p.cs == 0);
       const int ecw = (lane < 16) ? lane : wcols - 32 + lane;
       const bool evalid = (lane < 16) ? (wc0 + ecw < c0) : (wc0 + ecw > c1);
-      float epre[EPRE];
+      float2 eraw[EPRE];
       if (fast_edges) {
 #pragma unroll
         for (int k = 0; k < EPRE; ++k) {
           const int it = warp + k * NW;
-          epre[k] = 0.f;
-          if (it < NR && evalid) { const float2 o = __ldcg(objFc + (size_t)(r0 + it) * L + wc0 + ecw); epre[k] = fmaf(o.x, o.x, o.y * o.y); }
+          eraw[k] = make_float2(0.f, 0.f);
+          if (it < NR && evalid) eraw[k] = __ldcg(objFc + (size_t)(r0 + it) * L + wc0 + ecw);
         }
       }
       float pm2 = red[32];
 #pragma unroll
       for (int w = 1; w < NW; ++w) pm2 = fmaxf(pm2, red[32 + w]);
       const float inv_pmax = rsqrt_fast(pm2);                                  // 1 / max|P|
+      FPM_TICK(14);
       const int n = NR * NC;
-      int ir = tid / NC, jc = tid - ir * NC;
+      int ir = tq, jc = tr;
       constexpr int CU = Q_SMEM ? 2 : 6;                                       // elements in flight per thread
       for (int base = 0; base < n; base += CU * NT) {
         float2 Og[Q_SMEM ? 1 : CU];
@@ -569,11 +634,13 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
           if (jc >= NC) { jc -= NC; ++ir; }
         }
       }
+      FPM_TICK(15);
       if (fast_edges) {
 #pragma unroll
         for (int k = 0; k < EPRE; ++k) {
           const int it = warp + k * NW;
-          if (it < NR && evalid) W[(it << wsh) + ecw] = epre[k];
+          asm volatile("" : "+f"(eraw[k].x), "+f"(eraw[k].y));     // the loads are consumed here, not where they were issued
+          if (it < NR && evalid) W[(it << wsh) + ecw] = fmaf(eraw[k].x, eraw[k].x, eraw[k].y * eraw[k].y);
         }
         for (int it = warp + EPRE * NW; it < NR; it += NW)
           if (evalid) { const float2 o = __ldcg(objFc + (size_t)(r0 + it) * L + wc0 + ecw); W[(it << wsh) + ecw] = fmaf(o.x, o.x, o.y * o.y); }
@@ -663,7 +730,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       // ===== E: pupil update P += Q / max|objF| (fpmMain.cpp:470-475) as its own coalesced pass; max|P|^2 =====
       float pm2 = 0.f;
       constexpr int EU = 5;                          // Q loads in flight per thread
-      int ir = tid / NC, jc = tid - ir * NC;
+      int ir = tq, jc = tr;
       for (int base = tid; base < NR * NC; base += EU * NT) {
         float2 Qv[EU];
         {

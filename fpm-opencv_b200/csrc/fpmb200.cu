@@ -56,6 +56,7 @@ struct fpmb200_ctx {
   bool have_leds = false, have_support = false, have_stack = false;
   // kernel variant
   bool field_smem = false, p_smem = false, q_smem = false;
+  bool narrow = false;         // bbox within +-(3*R2-1): the pruned-butterfly instantiation of fpm_update_kernel (N = 128)
   int cs = 0;                  // log2 rows per max-cell
   size_t smem_bytes = 0;
   int max_smem_optin = 0, sm_count = 0;
@@ -237,7 +238,7 @@ static size_t update_smem_bytes(const fpmb200_ctx* c, bool field_smem, bool p_sm
   const size_t bb = sizeof(float2) * (size_t)(c->yhi - c->ylo + 1) * (c->xhi - c->xlo + 1);
   size_t b = 0;
   if (field_smem) b += (sizeof(float2) * N * PITCH + 15) / 16 * 16;
-  b += sizeof(float2) * N * 2 + sizeof(float) * 64;
+  b += sizeof(float4) * N * 2 + sizeof(float) * 64;                                   // twA, twB (twmul4 operands), red
   if (p_smem) b += bb;
   if (q_smem) {                                                                        // Qc + two TMA window buffers
     const int NRb = c->yhi - c->ylo + 1, ocp = ((c->xhi - c->xlo + 1) + 2) & ~1;
@@ -368,6 +369,10 @@ static int select_variant(fpmb200_ctx* c) {
   }
   if (!found) return fail(FPMB200_ERR_ARG, "update kernel does not fit %zu B of shared memory (Np=%d, Nlarge=%d)", cap, N, c->L);
   const int cs = c->cs;
+  {
+    const int lim = 3 * (N / 16) - 1;        // N = 128: R1 = 16, R2 = 8
+    c->narrow = (N == 128) && c->p_smem && c->q_smem && ylo >= -lim && yhi <= lim && xlo >= -lim && xhi <= lim;
+  }
   c->smem_bytes = update_smem_bytes(c, c->field_smem, c->p_smem, c->q_smem, cs);
   if (!c->field_smem && !c->field_gmem)
     CK(cudaMalloc(&c->field_gmem, sizeof(float2) * (size_t)N * (N + 1) * c->n_tiles));
@@ -392,8 +397,9 @@ static int select_variant(fpmb200_ctx* c) {
     c->have_tmap = true;
   }
   snprintf(c->variant, sizeof c->variant,
-           "fpm_update_kernel<N=%d,field=%s,pupil=%s,dP=%s> bbox=[%d..%d]x[%d..%d] maxcell=%dx16 smem=%zuB", N,
-           c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", c->q_smem ? "smem" : "field", ylo, yhi, xlo, xhi,
+           "fpm_update_kernel<N=%d,field=%s,pupil=%s,dP=%s%s> bbox=[%d..%d]x[%d..%d] maxcell=%dx16 smem=%zuB", N,
+           c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", c->q_smem ? "smem" : "field",
+           c->narrow ? ",pruned radix-16" : "", ylo, yhi, xlo, xhi,
            1 << cs, c->smem_bytes);
   return FPMB200_OK;
 }
@@ -492,7 +498,9 @@ template <int N, int NT, int MINB>
 static int launch_update(fpmb200_ctx* c, const UpdateParams& p, int n_blocks, cudaStream_t st) {
   void (*k)(const UpdateParams) = nullptr;   // (declared __grid_constant__ in the kernel)
   constexpr bool FS = (N <= 128);
-  if (c->p_smem && c->q_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, true>;
+  if constexpr (N == 128) { if (c->p_smem && c->q_smem && c->narrow) k = fpm_update_kernel<N, NT, MINB, FS, true, true, true>; }
+  if (k) {}
+  else if (c->p_smem && c->q_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, true>;
   else if (c->p_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, false>;
   else k = fpm_update_kernel<N, NT, MINB, FS, false, false>;
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));

@@ -29,12 +29,38 @@ template <int R, bool INV> double check() {
   return sqrt(err / nrm);
 }
 
+// fft16_in6 against fft16 on the zero-padded input (must agree exactly) and twmul4 against cmul / cmulc
+template <bool INV> int check_in6() {
+  srand(99 + INV);
+  int bad = 0;
+  for (int rep = 0; rep < 100; ++rep) {
+    float2 w[6], full[16], v[16];
+    for (int i = 0; i < 16; ++i) full[i] = make_float2(0.f, 0.f);
+    const int idx[6] = {0, 1, 2, 13, 14, 15};
+    for (int i = 0; i < 6; ++i) {
+      w[i] = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
+      full[idx[i]] = w[i];
+    }
+    fft16<INV>(full);
+    fft16_in6<INV>(w, v);
+    for (int i = 0; i < 16; ++i) bad += !(v[i].x == full[i].x && v[i].y == full[i].y);
+    const float2 a = w[0], t = w[1];
+    const float2 f = twmul4(a, make_float4(t.x, t.y, -t.y, t.x)), g = cmul(a, t);
+    // the packed device cmulc rounds a.y*b.x and fuses a.x*(-b.y) (the scalar host fallback fuses the other product)
+    const float2 fc = twmul4(a, make_float4(t.x, -t.y, t.y, t.x));
+    const float2 gc = make_float2(fmaf(a.x, t.x, a.y * t.y), fmaf(a.x, -t.y, a.y * t.x));
+    bad += !(f.x == g.x && f.y == g.y && fc.x == gc.x && fc.y == gc.y);
+  }
+  return bad;
+}
+
 int main() {
   double e[] = {check<2, false>(), check<2, true>(), check<3, false>(), check<3, true>(), check<4, false>(), check<4, true>(),
                 check<5, false>(), check<5, true>(), check<8, false>(), check<8, true>(), check<16, false>(), check<16, true>(),
                 check<32, false>(), check<32, true>()};
   const char* names[] = {"2f", "2i", "3f", "3i", "4f", "4i", "5f", "5i", "8f", "8i", "16f", "16i", "32f", "32i"};
-  int bad = 0;
+  int bad = check_in6<false>() + check_in6<true>();
+  printf("in6/twmul4 mismatches %d\n", bad);
   for (int i = 0; i < 14; ++i) { printf("%s %.3e\n", names[i], e[i]); bad += !(e[i] < 5e-7); }
   return bad;
 }

@@ -1,0 +1,19 @@
+"""Host-side check of the in-register butterflies (csrc/fft_regs.cuh are __host__ __device__): every radix against a
+naive float64 DFT, the pruned 16-point transform against the full one, table twiddles against cmul / cmulc."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="nvcc not available")
+def test_fft_regs_host(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "fft_regs_host_test")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-x", "cu", "-I", os.path.join(ROOT, "fpm-opencv_b200", "csrc"),
+                           "-o", exe, os.path.join(ROOT, "tests", "native", "fft_regs_host_test.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
