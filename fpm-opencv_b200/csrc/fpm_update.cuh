@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   constexpr int R1 = S::R1, R2 = S::R2, PITCH = S::PITCH, CH = S::CH;
   static_assert(!NARROW || (R1 == 16 && P_SMEM && Q_SMEM), "narrow-pupil specialisation");
   constexpr int H = N / 2, NW = NT / 32;
+  constexpr bool PIPE = !(FPM_EXP & 4);       // software-pipelined row passes (next item's loads ahead of this item's stores)
   extern __shared__ __align__(1024) unsigned char smem_raw[];   // TMA destinations need 128-byte alignment
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -224,12 +225,16 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     }
     return half_warp_max(cm, lane);
   };
-  // Row passes: work item g = tid + q*NT owns row g % N = tid % N (NT is a multiple of N), so the warps
-  // {w : w % (N/32) == b} own the 32 rows of block b in S3, S4 and S5 alike: a named barrier over those
-  // NT/N warps replaces the block-wide barrier between the row stages.
+  // Row passes: the WPB = NT/N consecutive warps {WPB*b .. WPB*b + WPB-1} own the 32 rows of block b in S3, S4 and
+  // S5 alike (lane = row inside the block, the warp's rank inside the group picks the sub-transforms), so a named
+  // barrier over those warps replaces the block-wide barrier between the row stages.  Consecutive warps sit on
+  // different SM sub-partitions: every scheduler holds one warp of each row block, and the blocks drift apart
+  // (one block's barrier wait is filled with another block's butterflies).
   static_assert(NT % N == 0 && N % 32 == 0 && N / 32 <= 15, "row-block barriers");
+  constexpr int WPB = NT / N;
+  const int rb_row = 32 * (warp / WPB) + lane, rb_sub = warp % WPB;
   auto row_block_sync = [&]() {
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp % (N / 32))), "r"(NT / N * 32) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / WPB), "r"(WPB * 32) : "memory");
   };
   // ---- prologue: tables, pupil -> shared memory, max|P|^2, max-cell grid, first window ----
   for (int t = tid; t < N; t += NT) {
@@ -404,9 +409,36 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       }
     }
     // ===== S3: rows stage A (inverse); columns outside the bbox are zero, not read.  Lanes run over rows. =====
-    for (int g = tid; g < N * R2; g += NT) {
-      const int row = g % N, j0 = g / N;
-      float2* rp = fld + row * PITCH + j0;
+    // (a thread's work items touch disjoint elements of its row, so the inputs of item q+1 are loaded before the
+    //  outputs of item q are stored: the shared-memory latency of the next item hides behind this item's butterfly)
+    if constexpr (NARROW && PIPE) {
+      constexpr int NI = R2 / WPB;
+      auto load6 = [&](int j0, float2 (&w)[6]) {
+        const float2* rp = fld + rb_row * PITCH + j0;
+        static_for<0, 6>([&](auto K) {
+          constexpr int k = decltype(K)::value;
+          constexpr int m = (k < 3) ? k : R1 - 6 + k;
+          const int jw = (k < 3) ? j0 + R2 * m : j0 + R2 * m - N;
+          w[k] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);       // (j0 is warp-uniform)
+        });
+      };
+      float2 wn[6];
+      load6(rb_sub, wn);
+      static_for<0, NI>([&](auto Q) {
+        constexpr int qi = decltype(Q)::value;
+        const int j0 = rb_sub + qi * WPB;
+        float2 w6[6], v[R1];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w6[k] = wn[k];
+        if constexpr (qi + 1 < NI) load6(j0 + WPB, wn);
+        fft16_in6<true>(w6, v);
+        float2* rp = fld + rb_row * PITCH + j0;
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul4(v[k1], twA[k1 * R2 + j0]);
+      });
+    } else
+    for (int j0 = rb_sub; j0 < R2; j0 += WPB) {
+      float2* rp = fld + rb_row * PITCH + j0;
       float2 v[R1];
       if constexpr (NARROW) {
         float2 w6[6];
@@ -432,25 +464,30 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     row_block_sync();          // S3 -> S4 -> S5 exchange data only within a block of 32 rows (= NT/N warps)
     FPM_TICK(3);
     // ===== S4: rows stage B (inverse) + amplitude replacement + rows stage B' (forward) =====
-    constexpr int S4R = (N * R1 + NT - 1) / NT;                 // work items per thread
+    constexpr int S4R = R1 / WPB;                               // work items per thread
+    static_assert(R1 % WPB == 0 && R2 % WPB == 0, "row work items per warp");
     constexpr bool S4PRE = (S4R * CH <= 8);                      // all 1/I up front when they fit 32 registers
     float4 ivall[S4PRE ? S4R : 1][CH];
     if constexpr (S4PRE) {
 #pragma unroll
       for (int rq = 0; rq < S4R; ++rq) {
-        const int g = tid + rq * NT;
-        if (g < N * R1) {
-          const float4* ip = reinterpret_cast<const float4*>(img) + (size_t)g * CH;   // permuted layout: item g owns R2 pixels
+        const int g = (rb_sub + rq * WPB) * N + rb_row;                // item (k1, row): index k1*N + row
+        const float4* ip = reinterpret_cast<const float4*>(img) + (size_t)g * CH;   // permuted layout: item g owns R2 pixels
 #pragma unroll
-          for (int c = 0; c < CH; ++c) ivall[rq][c] = __ldg(ip + c);
-        }
+        for (int c = 0; c < CH; ++c) ivall[rq][c] = __ldg(ip + c);
       }
+    }
+    constexpr bool PIPE4 = PIPE && (R2 <= 8);
+    float2 vnext[PIPE4 ? R2 : 1];
+    if constexpr (PIPE4) {
+      const float2* rp0 = fld + rb_row * PITCH + R2 * rb_sub;
+#pragma unroll
+      for (int a = 0; a < R2; ++a) vnext[a] = rp0[a];
     }
 #pragma unroll
     for (int rq = 0; rq < S4R; ++rq) {
-      const int g = tid + rq * NT;
-      if (g >= N * R1) break;
-      const int row = g % N, k1 = g / N;
+      const int k1 = rb_sub + rq * WPB, row = rb_row;
+      const int g = k1 * N + row;
       float4 iv[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
@@ -459,8 +496,17 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       }
       float2* rp = fld + row * PITCH + R2 * k1;
       float2 v[R2];
+      if constexpr (PIPE4) {
 #pragma unroll
-      for (int a = 0; a < R2; ++a) v[a] = rp[a];
+        for (int a = 0; a < R2; ++a) v[a] = vnext[a];
+        if (rq + 1 < S4R) {
+#pragma unroll
+          for (int a = 0; a < R2; ++a) vnext[a] = rp[R2 * WPB + a];      // item rq+1: k1 + WPB
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < R2; ++a) v[a] = rp[a];
+      }
       fftR<R2, true>(v);
 #pragma unroll
       for (int k2 = 0; k2 < R2; ++k2) {
@@ -479,9 +525,37 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     row_block_sync();
     FPM_TICK(4);
     // ================= S5: rows stage A' (forward) =================
-    for (int g = tid; g < N * R2; g += NT) {
-      const int row = g % N, q = g / N;
-      float2* rp = fld + row * PITCH + q;
+    if constexpr (NARROW && PIPE) {
+      constexpr int NI = R2 / WPB;
+      float2 vn[R1];
+      {
+        const float2* rp0 = fld + rb_row * PITCH + rb_sub;
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) vn[k1] = rp0[R2 * k1];
+      }
+      static_for<0, NI>([&](auto Q) {
+        constexpr int qi = decltype(Q)::value;
+        const int q = rb_sub + qi * WPB;
+        float2* rp = fld + rb_row * PITCH + q;
+        float2 v[R1];
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) v[k1] = vn[k1];
+        if constexpr (qi + 1 < NI) {
+#pragma unroll
+          for (int k1 = 0; k1 < R1; ++k1) vn[k1] = rp[WPB + R2 * k1];
+        }
+        fftR<R1, false>(v);
+        // S6, S7 and C2 read bbox columns only: six candidate outputs, the rest of the butterfly is dead code
+        static_for<0, 6>([&](auto K) {
+          constexpr int k = decltype(K)::value;
+          constexpr int r = (k < 3) ? k : R1 - 6 + k;
+          const int jw = (k < 3) ? q + R2 * r : q + R2 * r - N;
+          if (jw >= p.xlo && jw <= p.xhi) rp[R2 * r] = v[r];                            // (q is warp-uniform)
+        });
+      });
+    } else
+    for (int q = rb_sub; q < R2; q += WPB) {
+      float2* rp = fld + rb_row * PITCH + q;
       float2 v[R1];
 #pragma unroll
       for (int k1 = 0; k1 < R1; ++k1) v[k1] = rp[R2 * k1];
