@@ -236,6 +236,17 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   auto row_block_sync = [&]() {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / WPB), "r"(WPB * 32) : "memory");
   };
+  // Column stage B work items (k1, bbox column jc), R1 * NC of them.  A warp takes 32 consecutive columns of ONE k1
+  // (64 consecutive shared-memory words per access: no bank conflicts, k1 and its twiddles warp-uniform); the NC % 32
+  // left-over columns of every k1 are packed into a short second round, one item per thread (its index is computed
+  // once: an integer division on the per-update path of the critical warps costs more than the conflicts did).
+  const int cb_nfull = NC >> 5, cb_nl = NC & 31;
+  static_assert(R1 * 31 <= NT, "one left-over item per thread");
+  const int cb_k1 = tid / max(cb_nl, 1), cb_jc = (cb_nfull << 5) + tid % max(cb_nl, 1);
+  auto col_items_B = [&](auto&& body) {
+    for (int wi = warp; wi < R1 * cb_nfull; wi += NW) body(wi % R1, ((wi / R1) << 5) + lane);
+    if (cb_k1 < R1 && cb_nl) body(cb_k1, cb_jc);
+  };
   // ---- prologue: tables, pupil -> shared memory, max|P|^2, max-cell grid, first window ----
   for (int t = tid; t < N; t += NT) {
     const int b = t / R2, a = t % R2;
@@ -386,7 +397,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     __syncthreads();
     FPM_TICK(1);
     // ================= S2: cols stage B (inverse) =================
-    for (int g = tid, k1 = tq, jc = tr; g < R1 * NC; g += NT) {
+    col_items_B([&](int k1, int jc) {
       const int js = (p.xlo + jc) & (N - 1);
       float2 v[R2];
 #pragma unroll
@@ -394,8 +405,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       fftR<R2, true>(v);
 #pragma unroll
       for (int a = 0; a < R2; ++a) fld[(R2 * k1 + a) * PITCH + js] = v[a];
-      step_nt(k1, jc);
-    }
+    });
     __syncthreads();
     FPM_TICK(2);
     if constexpr (Q_SMEM) {
@@ -576,7 +586,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     __syncthreads();
     FPM_TICK(5);
     // ================= S6: cols stage B' (forward) =================
-    for (int g = tid, k1 = tq, jc = tr; g < R1 * NC; g += NT) {
+    col_items_B([&](int k1, int jc) {
       const int js = (p.xlo + jc) & (N - 1);
       float2 v[R2];
 #pragma unroll
@@ -584,8 +594,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       fftR<R2, false>(v);
 #pragma unroll
       for (int q = 0; q < R2; ++q) fld[(R2 * k1 + q) * PITCH + js] = twmul4(v[q], twB[q * R1 + k1]);
-      step_nt(k1, jc);
-    }
+    });
     __syncthreads();
     FPM_TICK(6);
     // ===== S7: cols stage A' (forward) -> Phi' in natural order; only bbox rows are stored (C2 reads nothing else) =====

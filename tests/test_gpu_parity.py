@@ -115,6 +115,30 @@ def test_full_run_parity_kappa0():
     ctx.close()
 
 
+@pytest.mark.parametrize("name,ctas", [("cfg1_mono_np64", 1), ("cfg2_fLEDc_np128", 1), ("cfg2_fLEDc_np128", 0), ("cfg7_mono_np90", 1)])
+def test_dark_and_saturated_pixels(name, ctas):
+    """Zero and full-scale intensities: sqrt(0) = 0 wipes the pixel (the device keeps 1/I = inf and must not produce
+    NaN), 65535 is the largest uint16 the loop reinterprets (fpmMain.cpp:380).  Whole dark images, dark rows, a
+    checkerboard of zeros and saturated blocks; every kernel family (fused, cluster, general path)."""
+    import copy
+    c = copy.copy(T.Case(name, 77, n_leds=24))
+    st_ = c.stack.copy()
+    st_[3] = 0                                   # a completely dark frame
+    st_[5, ::2, :] = 0                           # dark rows
+    st_[7, ::2, ::2] = 0; st_[7, 1::2, 1::2] = 0  # checkerboard
+    st_[9, :8, :8] = 65535                       # saturated block
+    st_[11] = 65535                              # a saturated frame
+    st_[13][st_[13] < np.median(st_[13])] = 0    # thresholded frame (typical after background subtraction)
+    c.stack = st_
+    ctx = c.make_ctx(cluster=ctas)
+    ctx.run(3)
+    ctx.finalize()
+    st = c.oracle_run(3)
+    e = compare(ctx, st)
+    print("%s dark/saturated: rel-L2 objF %.2e pupil %.2e [%s]" % (name, e[0], e[1], ctx.variant))
+    ctx.close()
+
+
 @pytest.mark.parametrize("name,n_leds,iters", [("cfg5b_cellscope2_np256", 40, 2), ("cfg3_cellScope_np256", 24, 1)])
 @pytest.mark.parametrize("ctas", [8, 1])
 def test_np256_tiles(name, n_leds, iters, ctas):
