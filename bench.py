@@ -49,12 +49,12 @@ def bytes_per_update(N):            # window read + write (fp32 compl
     return 18.0 * N * N
 
 
-def geometry():
+def geometry(cfg_json=None):
     """LED tables through the product's own host layer (C++ libfpmhost, not the oracle)."""
     import fpmhost
-    ds = fpmhost.Dataset(CFG_JSON, 10)
+    ds = fpmhost.Dataset(cfg_json or CFG_JSON, 10)
     s = ds.scalars
-    n = ds.geometry(1, min(293, s.ledCount))
+    n = ds.geometry(1, min(293, s.ledCount) if cfg_json is None else s.ledCount)
     cx, cy = ds.crop_tables()
     return dict(N=s.Np, L=s.Nlarge, r=s.naRadius, n_leds=n, cx=cx, cy=cy, delta1=s.delta1, delta2=s.delta2, eps=s.eps,
                 support=fpmhost.pupil_support(s.Np, s.naRadius))
@@ -280,6 +280,38 @@ def run_b200(args):
     fov_ms = sharding.max_over_ranks(f0.elapsed_time(f1), "cuda")
     gather_s = sharding.max_over_ranks(gather_ms, "cuda") * 1e-3
 
+    # ---- single-tile leg: BASELINE configs[1] (dataset_fLED-c.json optics, one 128x128 tile, 89 LEDs, pupil recovery on):
+    #      a latency number -- one tile is one thread-block cluster (4 SMs), the LED order is sequential ----
+    single = None
+    if rank == 0:
+        try:
+            import synth
+            g1 = geometry(os.path.join(ROOT, "configs", "cfg2_fLEDc_np128.json"))
+            c1 = fpmb200.Context(local)
+            c1.tiles_alloc(1, g1["N"], g1["L"], g1["n_leds"])
+            c1.set_params(g1["delta1"], g1["delta2"], g1["eps"], 1)
+            c1.upload_leds(g1["cx"], g1["cy"])
+            c1.upload_pupil_support(g1["support"])
+            c1.upload_stack(0, synth.synth_stack(g1["N"], g1["L"], g1["r"], g1["cx"], g1["cy"], 5000))
+            best = None
+            for rep in range(4):                      # first pass = warm-up
+                c1.init_tiles(0, 1, 1, sp)
+                s0, s1 = ev(), ev()
+                s0.record(main)
+                c1.run(iters, 0, 1, sp)
+                c1.finalize(0, 1, sp)
+                s1.record(main)
+                torch.cuda.synchronize()
+                if rep:
+                    best = min(best or 1e30, s0.elapsed_time(s1))
+            single = {"workload": "fLED-c optics (configs[1]), one 128x128 tile, Nlarge %d, %d LEDs, %d iterations" % (
+                          g1["L"], g1["n_leds"], iters),
+                      "recon_ms": best, "us_per_update": best * 1e3 / (g1["n_leds"] * iters),
+                      "updates_per_s": g1["n_leds"] * iters / (best * 1e-3), "kernel": c1.variant}
+            c1.close()
+        except Exception as e:                        # the headline legs above do not depend on this one
+            single = {"error": repr(e)}
+
     if rank == 0:
         peaks = {}
         try:
@@ -325,6 +357,8 @@ def run_b200(args):
             "full_fov": {"frame": "2560x2160", "tiles": fov_tiles, "recon_ms": fov_ms, "gather_s": gather_s,
                          "updates_per_s": fov_tiles * n_leds * iters / (fov_ms * 1e-3), "scaling": "strong"},
         }
+        if single is not None:
+            line["single_tile"] = single
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(g, distinct[0], iters)
         print(json.dumps(line), flush=True)
