@@ -874,14 +874,45 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   }
 }
 
-// Uploaded uint16 images -> 1/I as float in the device layout (one CTA per image; runs once per upload).
+// Uploaded uint16 images -> 1/I as float in the device layout (runs once per upload).  One CTA converts a band of
+// RB rows of one image: 16-byte loads of the uint16 rows, the permutation of stack_offset<N> goes through shared
+// memory (padded against bank conflicts), and the band leaves as contiguous runs of RUN floats (>= 128 bytes): both
+// sides of the copy are coalesced.  grid = (images, N / RB).
+template <int N> struct ConvertShape {
+  static constexpr int RB = (N * N <= 8192) ? N : 8192 / N;                 // rows per band (32 KB of floats)
+  static constexpr int NQ = RB / Shape<N>::R1;                              // values of y / R1 inside a band
+  static constexpr int RUN = NQ * Shape<N>::R2;                             // contiguous output floats per (x % R1, y % R1)
+  static_assert(RB % Shape<N>::R1 == 0 && (N % 8) == 0, "band shape");
+};
 template <int N>
 __global__ void __launch_bounds__(256) stack_convert_kernel(float* stack, const uint16_t* raw, long long first_image) {
-  const uint16_t* src = raw + (size_t)(first_image + blockIdx.x) * N * N;
+  using S = Shape<N>;
+  using CS = ConvertShape<N>;
+  constexpr int R1 = S::R1, R2 = S::R2, RB = CS::RB, RUN = CS::RUN, NB = RB * N;
+  __shared__ float buf[NB + NB / 32 + 32];
+  auto pad = [](int lo) { return lo + (lo >> 5) + ((lo >= NB / 2) ? 16 : 0); };
+  const int band = blockIdx.y;                                              // rows [band*RB, +RB): y / R1 = band*NQ + yq
+  const uint16_t* src = raw + ((size_t)(first_image + blockIdx.x) * N + (size_t)band * RB) * N;
   float* dst = stack + (size_t)(first_image + blockIdx.x) * N * N;
-  for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
-    const int y = t / N, x = t % N;
-    dst[stack_offset<N>(y, x)] = 1.0f / (float)src[t];       // 0 -> +inf: rsqrt(inf) = 0 = sqrt(0)
+  for (int t = threadIdx.x; t < NB / 8; t += 256) {                         // 8 pixels of one row per thread
+    const int yy = t / (N / 8), c = t - yy * (N / 8);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)yy * N) + c);
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+    const int ym = yy % R1, yq = yy / R1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int x = 8 * c + k;
+      const unsigned v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+      const int lo = ((x % R1) * R1 + ym) * RUN + yq * R2 + x / R1;
+      buf[pad(lo)] = 1.0f / (float)v;                                       // 0 -> +inf: rsqrt(inf) = 0 = sqrt(0)
+    }
+  }
+  __syncthreads();
+  for (int lo = threadIdx.x; lo < NB; lo += 256) {
+    const int r = lo / RUN, within = lo - r * RUN;
+    const int A = r / R1, ym = r - A * R1;                                  // A = x % R1
+    // stack_offset<N>(y, x) = ((x % R1) * N + R2 * (y % R1) + y / R1) * R2 + x / R1, with y / R1 = band*NQ + within / R2
+    dst[((size_t)A * N + R2 * ym + band * CS::NQ) * R2 + within] = buf[pad(lo)];
   }
 }
 

@@ -427,9 +427,9 @@ extern "C" int fpmb200_upload_stack(fpmb200_ctx* c, int first, int n, const uint
     const long long n_el = (long long)n_img * c->N * c->N;
     stack_convert_general<<<(int)((n_el + 256 * 8 - 1) / (256 * 8)), 256, 0, st>>>(c->stack, c->raw, first_img * c->N * c->N, n_el);
   } else switch (c->N) {
-    case 64: stack_convert_kernel<64><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
-    case 128: stack_convert_kernel<128><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
-    case 256: stack_convert_kernel<256><<<n_img, 256, 0, st>>>(c->stack, c->raw, first_img); break;
+    case 64: stack_convert_kernel<64><<<dim3(n_img, 64 / ConvertShape<64>::RB), 256, 0, st>>>(c->stack, c->raw, first_img); break;
+    case 128: stack_convert_kernel<128><<<dim3(n_img, 128 / ConvertShape<128>::RB), 256, 0, st>>>(c->stack, c->raw, first_img); break;
+    case 256: stack_convert_kernel<256><<<dim3(n_img, 256 / ConvertShape<256>::RB), 256, 0, st>>>(c->stack, c->raw, first_img); break;
   }
   c->launches++;
   CK(cudaGetLastError());
