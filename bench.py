@@ -39,6 +39,7 @@ WORKLOAD = "dogStomach optics (configs[3]), 128x128 tiles, Nlarge 384, 157 LEDs,
 METRIC = "sub-aperture updates/sec (aggregate over GPUs)"
 UNIT = "updates/s"
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12        # #SM * 128 lanes * 2 * f_max
+SMEM_PEAK_TBS_NOMINAL = 148 * 128 * 1.965e9 / 1e12              # #SM * 128 B/clk * f_max
 
 
 def flops_per_update(N):
@@ -354,6 +355,14 @@ def run_b200(args):
             "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
                               "frac": ach_tf / FP32_PEAK_TFLOPS_NOMINAL, "flops_per_update": flops_per_update(N),
                               "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (SURVEY 8d)"},
+            # SURVEY 8d's shared-memory lower bound (48*Np^2 bytes per update: one transpose per 2-D FFT + stage in/out)
+            # against 148 SMs x 128 B/clk x f_max; the ncu capture under profiles/ has the actual wavefront count
+            # (12.4 k per update = 61 % of the pipe: the unit that binds this kernel)
+            "roofline_smem": {"bound": "smem", "achieved": 48.0 * N * N * upd_per_launch / (kernel_ms * 1e-3) / 1e12,
+                              "peak": SMEM_PEAK_TBS_NOMINAL, "unit": "TB/s",
+                              "frac": 48.0 * N * N * upd_per_launch / (kernel_ms * 1e-3) / 1e12 / SMEM_PEAK_TBS_NOMINAL,
+                              "bytes_per_update": 48.0 * N * N,
+                              "peak_source": "nominal 148 SM x 128 B/clk x 1.965 GHz (SURVEY 8d)"},
             "full_fov": {"frame": "2560x2160", "tiles": fov_tiles, "recon_ms": fov_ms, "gather_s": gather_s,
                          "updates_per_s": fov_tiles * n_leds * iters / (fov_ms * 1e-3), "scaling": "strong"},
         }
