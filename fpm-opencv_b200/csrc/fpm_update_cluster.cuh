@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   const int jc0 = rank * CPC;
   const int ncl = max(0, min(CPC, NC - jc0));              // columns this CTA really has
   const int gc = L >> 4, gr = L >> p.cs;
+  // column work items (group, local column) of this thread: R1 * ncl <= 16 * 32 = NT, so every column stage is a single
+  // round and the item index is computed once (a runtime integer division per stage and update sits on the critical path)
+  static_assert(Shape<N>::R1 * 32 <= NT, "one column work item per thread");
+  const int tqc = ncl ? tid / ncl : 0, trc = ncl ? tid - tqc * ncl : 0;
+  const int qNTc = ncl ? NT / ncl : 0, rNTc = ncl ? NT % ncl : 0;               // t += NT without dividing
 
   const ClusterLayout<N, C> lay(NR, NC, CPC, L, p.cs);
   float2* rslab = reinterpret_cast<float2*>(smem_raw + lay.rslab);
@@ -208,16 +213,19 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     }
     // the cells this rectangle touches are rebuilt from scratch: their owners clear them now, the partial
     // maxima arrive after the third cluster barrier of this update
-    for (int t = tid; t < ncr * ncc; t += NT) {
-      const int a = cr0 + t / ncc, b = cc0 + t % ncc;
-      if (a % C == rank) U[(a / C) * gc + b] = 0.f;
+    // (cell columns padded to a power of two: shifts instead of a runtime integer division on the per-update path)
+    const int csh = 32 - __clz(ncc - 1);
+    for (int t = tid; t < (ncr << csh); t += NT) {
+      const int ta = t >> csh, tb = t & ((1 << csh) - 1);
+      const int a = cr0 + ta;
+      if (tb < ncc && a % C == rank) U[(a / C) * gc + cc0 + tb] = 0.f;
     }
 
     // ===== S1: pending pupil update (fpmMain.cpp:470-475), Phi = O*P, cols stage A (inverse) on this CTA's columns =====
     {
       float pm2 = 0.f;
-      for (int g = tid; g < R2 * ncl; g += NT) {        // work items packed densely over the lanes
-        const int i0 = g / ncl, jcl = g - i0 * ncl;
+      if (tid < R2 * ncl) {                              // work items packed densely over the lanes
+        const int i0 = tqc, jcl = trc;
         {
           float2 v[R1];
           // Branch-free: rows outside the bbox read a clamped (valid) address and are zeroed afterwards, so the R1
@@ -260,8 +268,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       if (lane < C) st_async_f1(mapa_u32(pmx_a + 4u * rank, lane), m, mapa_u32(rbar_a, lane));
     }
     // ===== S2: cols stage B (inverse); the results go to the owners of the row positions =====
-    for (int g = tid; g < R1 * ncl; g += NT) {
-      const int k1 = g / ncl, jcl = g - k1 * ncl;
+    if (tid < R1 * ncl) {
+      const int k1 = tqc, jcl = trc;
       {
         const int js = (p.xlo + jc0 + jcl) & (N - 1);
         float2 v[R2];
@@ -374,8 +382,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
 #pragma unroll
     for (int k = 1; k < C; ++k) pm2c = fmaxf(pm2c, pmx[k]);
     // ===== S6: cols stage B' (forward) =====
-    for (int g = tid; g < R1 * ncl; g += NT) {
-      const int k1 = g / ncl, jcl = g - k1 * ncl;
+    if (tid < R1 * ncl) {
+      const int k1 = tqc, jcl = trc;
       {
         float2* cp = cslab + jcl * PR + R2 * k1;
         float2 v[R2];
@@ -389,8 +397,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     __syncthreads();
     FPM_TICK(6);
     // ===== S7: cols stage A' (forward) -> Phi' in natural row order; only bbox rows are stored =====
-    for (int g = tid; g < R2 * ncl; g += NT) {
-      const int q = g / ncl, jcl = g - q * ncl;
+    if (tid < R2 * ncl) {
+      const int q = tqc, jcl = trc;
       {
         float2* cp = cslab + jcl * PR;
         float2 v[R1];
@@ -413,8 +421,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       float2* wr = objFc + (size_t)r0 * L + c0 + jc0;
       constexpr int UN = (N == 256) ? 9 : 6;                // window elements in flight per thread
       const int n = NR * ncl;
-      const int qNT = ncl ? NT / ncl : 0, rNT = ncl ? NT % ncl : 0;     // t += NT without dividing
-      int ir0 = ncl ? tid / ncl : 0, jl0 = ncl ? tid - ir0 * ncl : 0;
+      const int qNT = qNTc, rNT = rNTc;
+      int ir0 = tqc, jl0 = trc;
       for (int base = tid; base < n; base += UN * NT) {
         float2 Ov[UN];
         {
@@ -463,8 +471,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     if (ncl > 0) {
       const int ca0 = c0 + jc0, ca1 = ca0 + ncl - 1;                    // absolute columns of the slice
       const int lcc0 = ca0 >> 4, nlc = (ca1 >> 4) - lcc0 + 1;
-      for (int t = tid; t < NR * nlc; t += NT) {
-        const int ir = t / nlc, bl = t - ir * nlc;
+      const int lsh = 32 - __clz(nlc - 1);
+      for (int t = tid; t < (NR << lsh); t += NT) {
+        const int ir = t >> lsh, bl = t & ((1 << lsh) - 1);
+        if (bl >= nlc) continue;
         const int lo = max(ca0, (lcc0 + bl) << 4), hi = min(ca1, ((lcc0 + bl) << 4) + 15);
         const float* wp = W + ir * CPC - ca0;
         float m = 0.f;
@@ -476,10 +486,15 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     // cluster): strips above / below (full width of the touched cells) and left / right (rectangle rows)
     {
       const int wc0 = cc0 << 4, wcols = ncc << 4, rt0 = cr0 << p.cs, rt1 = ((cr0 + ncr) << p.cs) - 1;
-      const int n_top = (r0 - rt0) * wcols, n_bot = (rt1 - r1) * wcols;
       const int wl = c0 - wc0, wrt = wc0 + wcols - 1 - c1;
-      const int n_left = NR * wl, n_right = NR * wrt;
-      const int n_all = n_top + n_bot + n_left + n_right;
+      // Strip items.  When they fit one item per thread of the cluster even with padded widths (2^wsh2 for the
+      // full-width strips, 16 for the side strips) the index is split with shifts; a runtime integer division on the
+      // per-update path costs more than the idle lanes.  Large rectangles keep the dense enumeration.
+      const int wsh2 = 32 - __clz(wcols - 1), wmask = (1 << wsh2) - 1;
+      const int P1 = (r0 - rt0) << wsh2, P2 = P1 + ((rt1 - r1) << wsh2), P3 = P2 + (NR << 4), n_pad = P3 + (NR << 4);
+      const bool padded = n_pad <= C * NT;
+      const int n_top = (r0 - rt0) * wcols, n_bot = (rt1 - r1) * wcols, n_left = NR * wl, n_right = NR * wrt;
+      const int n_all = padded ? n_pad : n_top + n_bot + n_left + n_right;
       constexpr int DU = 4;
       for (int base = rank * NT + tid; base < n_all; base += DU * C * NT) {
         float2 o[DU];
@@ -490,10 +505,19 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
           cell[k] = -1;
           if (t < n_all) {
             int r, c;
-            if (t < n_top) { r = rt0 + t / wcols; c = wc0 + t % wcols; }
-            else if (t < n_top + n_bot) { const int s = t - n_top; r = r1 + 1 + s / wcols; c = wc0 + s % wcols; }
-            else if (t < n_top + n_bot + n_left) { const int s = t - n_top - n_bot; r = r0 + s / wl; c = wc0 + s % wl; }
-            else { const int s = t - n_top - n_bot - n_left; r = r0 + s / wrt; c = c1 + 1 + s % wrt; }
+            if (padded) {
+              bool ok;
+              if (t < P1) { const int cc = t & wmask; r = rt0 + (t >> wsh2); c = wc0 + cc; ok = cc < wcols; }
+              else if (t < P2) { const int s = t - P1, cc = s & wmask; r = r1 + 1 + (s >> wsh2); c = wc0 + cc; ok = cc < wcols; }
+              else if (t < P3) { const int s = t - P2, cc = s & 15; r = r0 + (s >> 4); c = wc0 + cc; ok = cc < wl; }
+              else { const int s = t - P3, cc = s & 15; r = r0 + (s >> 4); c = c1 + 1 + cc; ok = cc < wrt; }
+              if (!ok) continue;
+            } else {
+              if (t < n_top) { r = rt0 + t / wcols; c = wc0 + t % wcols; }
+              else if (t < n_top + n_bot) { const int s = t - n_top; r = r1 + 1 + s / wcols; c = wc0 + s % wcols; }
+              else if (t < n_top + n_bot + n_left) { const int s = t - n_top - n_bot; r = r0 + s / wl; c = wc0 + s % wl; }
+              else { const int s = t - n_top - n_bot - n_left; r = r0 + s / wrt; c = c1 + 1 + s % wrt; }
+            }
             o[k] = __ldcg(objFc + (size_t)r * L + c);
             cell[k] = ((r >> p.cs) - cr0) * tmc + ((c >> 4) - cc0);
           }
@@ -507,8 +531,9 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
 #ifdef FPM_STAGE_TIMING
     FPM_TICK(12);
 #endif
-    for (int t = tid; t < ncr * ncc; t += NT) {              // merge into the owners' grids
-      const int ta = t / ncc, tb = t - ta * ncc;
+    for (int t = tid; t < (ncr << csh); t += NT) {           // merge into the owners' grids
+      const int ta = t >> csh, tb = t & ((1 << csh) - 1);
+      if (tb >= ncc) continue;
       const unsigned v = Tm[ta * tmc + tb];
       Tm[ta * tmc + tb] = 0u;
       if (v) {

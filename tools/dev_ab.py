@@ -23,4 +23,4 @@ for rep in range(reps):
         res[l].append(iters * len(c.cx) * n_tiles / dt)
         ctx.close()
 for l in libs:
-    print("%-28s %s  best %.3f M upd/s" % (l, " ".join("%.3f" % (v / 1e6) for v in res[l]), max(res[l]) / 1e6))
+    print("%-28s %s  best %.4f M upd/s" % (l, " ".join("%.4f" % (v / 1e6) for v in res[l]), max(res[l]) / 1e6))
