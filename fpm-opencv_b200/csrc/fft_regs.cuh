@@ -278,4 +278,65 @@ template <int R, bool INV> __host__ __device__ __forceinline__ void fftR(float2 
   else static_assert(R == 16, "unsupported radix");
 }
 
+// ---- composite radices 6, 9, 10 (mixed-radix tiles: Np = 90 = 9 x 10, 100 = 10 x 10 ...) --------------------------
+// cos / sin by Taylor series in double, for compile-time roots of unity (|x| <= pi: 17 terms reach 1e-16)
+__host__ __device__ constexpr double cx_cos(double x) {
+  double s = 1.0, t = 1.0;
+  for (int k = 1; k <= 17; ++k) { t *= -x * x / ((2.0 * k - 1.0) * (2.0 * k)); s += t; }
+  return s;
+}
+__host__ __device__ constexpr double cx_sin(double x) {
+  double s = x, t = x;
+  for (int k = 1; k <= 17; ++k) { t *= -x * x / ((2.0 * k) * (2.0 * k + 1.0)); s += t; }
+  return s;
+}
+// angle of the m-th R-th root of unity, folded into (-pi, pi]
+__host__ __device__ constexpr double root_angle(int m, int R) {
+  int q = m % R;
+  if (2 * q > R) q -= R;
+  return 6.283185307179586476925286766559 * q / R;
+}
+
+// R = A * B Cooley-Tukey split; B == 1: a direct butterfly
+template <int R> struct RadixSplit { static constexpr int A = R, B = 1; };
+template <> struct RadixSplit<6> { static constexpr int A = 2, B = 3; };
+template <> struct RadixSplit<9> { static constexpr int A = 3, B = 3; };
+template <> struct RadixSplit<10> { static constexpr int A = 2, B = 5; };
+// fft_reg<R> leaves X[radix_out<R>(i)] in v[i] (slot B*k1 + k2 holds X[k1 + A*k2]); the caller folds the permutation
+// into its store addresses
+template <int R> __host__ __device__ constexpr int radix_out(int i) {
+  return RadixSplit<R>::B == 1 ? i : i / RadixSplit<R>::B + RadixSplit<R>::A * (i % RadixSplit<R>::B);
+}
+
+// n-point butterfly over v[O], v[O+S], ...
+template <int n, bool INV, int O, int S, int R> __host__ __device__ __forceinline__ void fft_strided(float2 (&v)[R]) {
+  if constexpr (n == 2) fft2<INV>(v[O], v[O + S]);
+  else if constexpr (n == 3) fft3<INV>(v[O], v[O + S], v[O + 2 * S]);
+  else if constexpr (n == 4) fft4<INV>(v[O], v[O + S], v[O + 2 * S], v[O + 3 * S]);
+  else if constexpr (n == 5) fft5<INV>(v[O], v[O + S], v[O + 2 * S], v[O + 3 * S], v[O + 4 * S]);
+  else static_assert(n == 2, "unsupported butterfly");
+}
+
+template <int R, bool INV> __host__ __device__ __forceinline__ void fft_reg(float2 (&v)[R]) {
+  constexpr int A = RadixSplit<R>::A, B = RadixSplit<R>::B;
+  if constexpr (B == 1) {
+    if constexpr (R == 8) fft8<INV>(v);
+    else if constexpr (R == 16) fft16<INV>(v);
+    else fft_strided<R, INV, 0, 1>(v);
+  } else {
+    // input index n = B*a + b: for every b an A-point transform over a (k1 lands in slot B*k1 + b) ...
+    static_for<0, B>([&](auto Bq) { fft_strided<A, INV, decltype(Bq)::value, B>(v); });
+    // ... twiddled by W_R^(b*k1) ...
+    static_for<1, A>([&](auto K1) {
+      static_for<1, B>([&](auto Bq) {
+        constexpr int k1 = decltype(K1)::value, b = decltype(Bq)::value;
+        constexpr float c = (float)cx_cos(root_angle(k1 * b, R)), s = (float)cx_sin(root_angle(k1 * b, R));
+        v[B * k1 + b] = twmul<INV>(v[B * k1 + b], make_float2(c, -s));
+      });
+    });
+    // ... then for every k1 a B-point transform over b: slot B*k1 + k2 = X[k1 + A*k2]
+    static_for<0, A>([&](auto K1) { fft_strided<B, INV, B * decltype(K1)::value, 1>(v); });
+  }
+}
+
 }  // namespace fpm

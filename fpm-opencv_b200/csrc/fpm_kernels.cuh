@@ -7,6 +7,7 @@
 #include "fpm_update.cuh"
 #include "fpm_update_cluster.cuh"
 #include "fpm_general.cuh"
+#include "fpm_general_fused.cuh"
 #include "fpm_fov.cuh"
 
 namespace fpm {

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -67,6 +68,7 @@ struct fpmb200_ctx {
   int ocp = 0;
   // general (unfused) path for tile sizes other than 64/128/256
   bool general = false;
+  bool gfused = false;         // general sizes whose field fits shared memory twice: fpm_update_general_kernel
   float2* gfield = nullptr;    // [n_tiles][N][N]
   float2* gq = nullptr;        // [n_tiles][N][N]
   float* gcells = nullptr;     // [n_tiles][cgr][cgc]
@@ -91,6 +93,8 @@ struct fpmb200_ctx {
 };
 
 static int select_variant(fpmb200_ctx* c);
+static void factorize(int n, fpm::LineFFTParams& p);
+static int general_fused_plan(int N);
 
 extern "C" const char* fpmb200_last_error(void) { return g_err.c_str(); }
 extern "C" int fpmb200_abi_version(void) { return 1; }
@@ -313,6 +317,25 @@ static int select_variant(fpmb200_ctx* c) {
     if (c->cluster_req > 1) return fail(FPMB200_ERR_ARG, "cluster kernels exist for Np = 128 and 256 only (Np=%d)", N);
     c->cluster = 1;
     c->cgr = c->cgc = (c->L + 15) / 16;
+    // one CTA per tile with the field in shared memory when two copies of it fit (Np 90, 100 of the shipped JSONs);
+    // FPMB200_GENERAL_UNFUSED=1 keeps the per-step kernels, FPMB200_GENERAL_PLAN=0 the run-time radices (developer A/B)
+    LineFFTParams fp;
+    factorize(N, fp);
+    {
+      const char* e = getenv("FPMB200_GENERAL_UNFUSED");
+      c->gfused = fp.nrad <= 8 && general_fused_smem_bytes(N, c->cgr, c->cgc) <= (size_t)c->max_smem_optin && !(e && e[0] == '1');
+    }
+    if (c->gfused) {
+      c->smem_bytes = general_fused_smem_bytes(N, c->cgr, c->cgc);
+      const int plan = general_fused_plan(N);
+      char radices[48];
+      if (plan) snprintf(radices, sizeof radices, "radix %d x %d in registers, M and C fused into the column stages", plan / 100, plan % 100);
+      else snprintf(radices, sizeof radices, "run-time radices, %d stages", fp.nrad);
+      snprintf(c->variant, sizeof c->variant,
+               "general path, fused: fpm_update_general_kernel (one CTA per tile, field in shared memory, Stockham %s) "
+               "Np=%d Nlarge=%d maxcell=16x16 smem=%zuB", radices, N, c->L, c->smem_bytes);
+      return FPMB200_OK;
+    }
     if (!c->gfield) {
       const size_t NN = (size_t)N * N;
       CK(cudaMalloc(&c->gfield, sizeof(float2) * NN * c->n_tiles));
@@ -535,7 +558,53 @@ static void drop_graphs(fpmb200_ctx* c) {
   c->iter_graphs.clear();
 }
 
+// R1 * 100 + R2 of the compiled two-stage plan for Np, 0 if there is none
+static int general_fused_plan(int N) {
+  const char* e = getenv("FPMB200_GENERAL_PLAN");
+  if (e && e[0] == '0') return 0;
+  switch (N) {
+    case 90: return 1009;
+    case 100: return 1010;
+    case 80: return 1008;
+    case 72: return 908;
+    case 96: return 1606;
+    case 60: return 1006;
+    default: return 0;
+  }
+}
+
+static int run_updates_general_fused(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
+  GeneralFusedParams p;
+  memset(&p, 0, sizeof p);
+  p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop; p.tw = c->twN;
+  p.N = c->N; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first; p.slot_begin = slot_begin; p.n_updates = n_updates;
+  p.cgr = c->cgr; p.cgc = c->cgc;
+  p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
+  LineFFTParams fp;
+  factorize(c->N, fp);
+  p.nrad = fp.nrad;
+  for (int s = 0; s < fp.nrad; ++s) p.rad[s] = fp.rad[s];
+  // two-stage plans with compile-time radices for the sizes of the shipped JSONs (and their neighbours); other sizes
+  // take the radices at run time
+  void (*k)(const GeneralFusedParams) = fpm_update_general_kernel<512, 0, 0>;
+  switch (general_fused_plan(c->N)) {
+    case 1009: k = fpm_update_general_kernel<512, 10, 9>; break;
+    case 1010: k = fpm_update_general_kernel<512, 10, 10>; break;
+    case 1008: k = fpm_update_general_kernel<512, 10, 8>; break;
+    case 908: k = fpm_update_general_kernel<512, 9, 8>; break;
+    case 1606: k = fpm_update_general_kernel<512, 16, 6>; break;
+    case 1006: k = fpm_update_general_kernel<512, 10, 6>; break;
+    default: break;
+  }
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  k<<<n, 512, c->smem_bytes, st>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  return FPMB200_OK;
+}
+
 static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
+  if (c->gfused) return run_updates_general_fused(c, first, n, slot_begin, n_updates, st);
   GeneralParams p;
   memset(&p, 0, sizeof p);
   const int N = c->N;

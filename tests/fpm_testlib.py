@@ -64,6 +64,28 @@ class Case:
         return ctx
 
 
+class SyntheticCase(Case):
+    """A tile size no shipped JSON uses: Np and Nlarge chosen freely, windows on a seeded spiral around the centre
+    (brightfield first, like the NA-sorted order of the reference); parameters of cfg7."""
+
+    def __init__(self, N, factor, seed, n_leds):
+        j = orc.load_json_lenient(embedded_path("cfg7_mono_np90"))
+        self.name, self.cfg = "synthetic_np%d" % N, orc.config_from_json(j)
+        self.N, self.L, self.r = N, N * factor, max(3, N // 6)
+        rng = np.random.default_rng(seed)
+        c0 = (self.L - N) // 2
+        k = np.arange(n_leds)
+        rad = np.minimum(c0, 0.35 * self.r * np.sqrt(k))
+        ang = 2.4 * k + rng.random(n_leds)
+        self.cx = np.clip(np.rint(c0 + rad * np.cos(ang)), 0, self.L - N).astype(np.int16)
+        self.cy = np.clip(np.rint(c0 + rad * np.sin(ang)), 0, self.L - N).astype(np.int16)
+        self.cx[:2] = c0
+        self.cy[:2] = c0
+        self.order = list(range(n_leds))
+        self.stack = synth.synth_stack(N, self.L, self.r, self.cx, self.cy, seed)
+        self.support = orc.pupil_support(N, self.r)
+
+
 @functools.lru_cache(maxsize=16)
 def case(name, seed=1234, n_leds=None):
     return Case(name, seed, n_leds)

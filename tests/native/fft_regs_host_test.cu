@@ -16,7 +16,12 @@ template <int R, bool INV> double check() {
   }
   if constexpr (R == 3) fft3<INV>(v[0], v[1], v[2]);
   else if constexpr (R == 5) fft5<INV>(v[0], v[1], v[2], v[3], v[4]);
-  else fftR<R, INV>(v);
+  else if constexpr (R == 6 || R == 9 || R == 10) {
+    float2 w[R];
+    fft_reg<R, INV>(v);                                  // permuted output: slot i holds X[radix_out<R>(i)]
+    for (int i = 0; i < R; ++i) w[radix_out<R>(i)] = v[i];
+    for (int i = 0; i < R; ++i) v[i] = w[i];
+  } else fftR<R, INV>(v);
   double err = 0, nrm = 0;
   for (int k = 0; k < R; ++k) {
     double sr = 0, si = 0;
@@ -57,10 +62,11 @@ template <bool INV> int check_in6() {
 int main() {
   double e[] = {check<2, false>(), check<2, true>(), check<3, false>(), check<3, true>(), check<4, false>(), check<4, true>(),
                 check<5, false>(), check<5, true>(), check<8, false>(), check<8, true>(), check<16, false>(), check<16, true>(),
-                check<32, false>(), check<32, true>()};
-  const char* names[] = {"2f", "2i", "3f", "3i", "4f", "4i", "5f", "5i", "8f", "8i", "16f", "16i", "32f", "32i"};
+                check<32, false>(), check<32, true>(), check<6, false>(), check<6, true>(), check<9, false>(), check<9, true>(),
+                check<10, false>(), check<10, true>()};
+  const char* names[] = {"2f", "2i", "3f", "3i", "4f", "4i", "5f", "5i", "8f", "8i", "16f", "16i", "32f", "32i", "6f", "6i", "9f", "9i", "10f", "10i"};
   int bad = check_in6<false>() + check_in6<true>();
   printf("in6/twmul4 mismatches %d\n", bad);
-  for (int i = 0; i < 14; ++i) { printf("%s %.3e\n", names[i], e[i]); bad += !(e[i] < 5e-7); }
+  for (int i = 0; i < 20; ++i) { printf("%s %.3e\n", names[i], e[i]); bad += !(e[i] < 5e-7); }
   return bad;
 }

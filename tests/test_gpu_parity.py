@@ -167,7 +167,7 @@ def test_against_committed_opencv_fixtures(path):
     ctx.close()
 
 
-# ---- the shipped JSONs with their literal cropSizeX (90, 100, 200): general, unfused path ---------
+# ---- the shipped JSONs with their literal cropSizeX (90, 100: fused general kernel; 200: unfused path) ---------
 @pytest.mark.parametrize("name,n_leds,iters", [("cfg7_mono_np90", 117, 3), ("cfg8_cellScope_np100", 60, 2),
                                                ("cfg4s_dogStomach_np200", 40, 2)])
 @pytest.mark.parametrize("kappa", [1, 0])
@@ -194,6 +194,48 @@ def test_literal_tile_sizes(name, n_leds, iters, kappa):
     e = compare(ctx, c.oracle_run(iters, kappa=kappa))
     print("%s kappa=%d per-step %.2e, %d iterations: objF %.2e pupil %.2e" % (name, kappa, worst, iters, e[0], e[1]))
     ctx.close()
+
+
+@pytest.mark.parametrize("N,factor,expect", [(60, 4, "radix 10 x 6"), (72, 3, "radix 9 x 8"), (80, 3, "radix 10 x 8"),
+                                             (96, 3, "radix 16 x 6"), (50, 4, "run-time radices"), (108, 3, "run-time radices")])
+def test_general_fused_other_sizes(N, factor, expect):
+    """Every compiled two-stage radix plan of fpm_update_general_kernel besides the shipped 90 / 100, and the run-time
+    radix variant (Np = 50 = 2*5*5, 108 = 4*3*3*3): per-step and full-run parity on synthetic geometry."""
+    c = T.SyntheticCase(N, factor, 100 + N, 24)
+    ctx = c.make_ctx()
+    assert "general path, fused" in ctx.variant and expect in ctx.variant, ctx.variant
+    st = orc.init_state(c.stack, c.L, c.r)
+    for k in range(len(c.cx)):
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+    for k in range(6):
+        ctx.upload_state(0, T.corner(st.objFc), st.P)
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+        ctx.step(0, k)
+        compare(ctx, st, tol=STEP_TOL, crop=False)
+    ctx.init_tiles()
+    ctx.run(3)
+    ctx.finalize()
+    compare(ctx, c.oracle_run(3))
+    ctx.close()
+
+
+def test_general_fused_variants_agree(monkeypatch):
+    """Np = 90: the two-stage plan, the run-time radices and the unfused per-step kernels are three implementations of
+    the same update; each within the full-run tolerance of the oracle (checked against one oracle run)."""
+    c = T.Case("cfg7_mono_np90", 5, 40)
+    ref = c.oracle_run(2)
+    for env, expect in (({}, "radix 10 x 9"), ({"FPMB200_GENERAL_PLAN": "0"}, "run-time radices"),
+                        ({"FPMB200_GENERAL_UNFUSED": "1"}, "unfused")):
+        for k in ("FPMB200_GENERAL_PLAN", "FPMB200_GENERAL_UNFUSED"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = c.make_ctx()
+        assert expect in ctx.variant, ctx.variant
+        ctx.run(2)
+        ctx.finalize()
+        compare(ctx, ref)
+        ctx.close()
 
 
 def test_general_path_many_tiles():
