@@ -41,7 +41,9 @@ struct GeneralFusedParams {
   int slot_begin, n_updates;
   int cgr, cgc;             // grid of 16x16-pixel max-cells over the spectrum (edge cells partial)
   int nrad, rad[8];         // transform stages
+  int ylo, yhi, xlo, xhi;   // bounding box of the pupil support, wrapped indices in [-N/2, N/2)
   float delta1, delta2, eps, kappa;
+  long long* stage_clk;     // [16] per-stage cycle totals of CTA 0 (only with -DFPM_STAGE_TIMING)
 };
 
 __host__ __device__ inline size_t general_fused_smem_bytes(int N, int cgr, int cgc) {
@@ -49,49 +51,39 @@ __host__ __device__ inline size_t general_fused_smem_bytes(int N, int cgr, int c
   return 2 * fld + sizeof(float2) * N + sizeof(float) * ((size_t)cgr * cgc + 64) + 32;
 }
 
-// What the fused column stages need besides the field (MODE 1: amplitude replacement, MODE 2: object / pupil increments)
+// What the column stages with an epilogue need besides the field
 struct StageExtra {
   const float* inv_i;                 // MODE 1: 1/I of this LED, [N][N]
-  float2* O;                          // MODE 2: window origin in the centred spectrum (wrapped indices -H .. H-1)
-  const float2* P;                    // MODE 2: pupil [N][N]
-  const float* support;               // MODE 2: [N][N]
-  int L;
-  float epsr, epsi, delta1, delta2, kd1, kd2, inv_pmax;
+  int ylo, yhi;                       // MODE 2: wrapped row range of the support's bounding box
+  float epsr, epsi;                   // MODE 1
 };
 
 // One Stockham stage of a two-stage plan N = R1 * R2 over all N lines, src -> dst, radix R at compile time: each work
 // item is one R-point transform in registers (fft_reg, composite radices 6 / 9 / 10 included).  FIRST: radix R1, no
 // twiddles, outputs contiguous (j*R + k); otherwise radix R2, inputs twiddled by W_N^(r*j), outputs at j + k*R1.
-// Work item t = j * N + l: lanes over lines.  MODE 1 / 2 (column stages only: es = pitch, ls = 1, so lanes run over
-// columns and every global access below is coalesced) fuse the pointwise step that follows the transform into the
-// stores: M (amplitude replacement, fpmMain.cpp:378-393) resp. C (object update written to the spectrum, pupil increment
-// Q left in dst in place of Phi', :406-447, 459-472); their global operands are requested before the butterflies.
+// Work item t = j * nl + li over the nl lines l0 .. l0+nl-1 (wrapped indices; all lines: l0 = 0, nl = N): lanes over
+// lines.  Lines outside the bounding box of the pupil support are skipped where they are known to be zero (row
+// transforms of O * P) or not needed (column transforms of Phi').  MODE 1 / 2 (column stages only: es = pitch, ls = 1, so lanes run over
+// columns and the global loads are coalesced): MODE 1 fuses M (amplitude replacement, fpmMain.cpp:378-393) into the
+// stores, its 1/I operands requested before the butterflies; MODE 2 is the last forward stage: only the box of Phi' is
+// kept, everything else of dst is zeroed (C runs as its own pass over the box: fused into this stage it was
+// issue-bound on an unbalanced 1.2 rounds of work items, 13 k cycles against 2 k + 3 k separately).
 template <int NT, int R, bool INV, bool FIRST, int MODE>
 __device__ __forceinline__ void plan_stage(const float2* __restrict__ src, float2* __restrict__ dst,
                                            const float2* __restrict__ tws, int N, int es, int ls, int tid,
-                                           const StageExtra& x) {
-  const int T = N / R, total = N * T;
-  const int qNT = NT / N, rNT = NT % N;
-  int j = tid / N, l = tid % N;
+                                           int l0, int nl, const StageExtra& x) {
+  const int T = N / R, total = nl * T;
+  const int qNT = NT / nl, rNT = NT % nl;
+  int j = tid / nl, li = tid % nl;
   for (int t = tid; t < total; t += NT) {
+    int l = l0 + li;                                     // wrapped line index -> natural
+    if (l < 0) l += N;
     float2 v[R];
     float ii[MODE == 1 ? R : 1];
-    float2 Ov[MODE == 2 ? R : 1], Pv[MODE == 2 ? R : 1];
-    int oo[MODE == 2 ? R : 1];
     if constexpr (MODE == 1) {
       static_for<0, R>([&](auto I) {
         constexpr int i = decltype(I)::value;
         ii[i] = __ldg(x.inv_i + (j + radix_out<R>(i) * T) * N + l);
-      });
-    }
-    if constexpr (MODE == 2) {
-      const int wl = wrap_half(l, N);
-      static_for<0, R>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        const int row = j + radix_out<R>(i) * T;
-        oo[i] = wrap_half(row, N) * x.L + wl;
-        Ov[i] = x.O[oo[i]];
-        Pv[i] = x.P[row * N + l];
       });
     }
     const float2* s = src + l * ls + j * es;
@@ -111,31 +103,31 @@ __device__ __forceinline__ void plan_stage(const float2* __restrict__ src, float
         const float sc = rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y) * ii[i]);          // sqrt(I)/|psi+eps|; I = 0 -> 0
         val = make_float2(val.x * sc, val.y * sc);
       }
-      if constexpr (MODE == 2) {
-        const float2 O0 = Ov[i], P0 = Pv[i];
-        const float sup = __ldg(x.support + (j + ko * T) * N + l);
-        const float2 dd = csub(val, cmul(O0, P0));
-        const float pa2 = fmaf(P0.x, P0.x, P0.y * P0.y);
-        const float2 num = cmulc(dd, P0);
-        const float A = pa2 + x.delta2;
-        const float sc = __fdividef(sqrt_fast(pa2) * x.inv_pmax, fmaf(A, A, x.kd2 * x.kd2));
-        x.O[oo[i]] = make_float2(O0.x + (num.x * A + num.y * x.kd2) * sc, O0.y + (num.y * A - num.x * x.kd2) * sc);
-        const float oa2 = fmaf(O0.x, O0.x, O0.y * O0.y);
-        const float2 numq = cmulc(dd, O0);
-        const float A1 = oa2 + x.delta1;
-        const float sq = __fdividef(sqrt_fast(oa2) * sup, fmaf(A1, A1, x.kd1 * x.kd1));
-        val = make_float2((numq.x * A1 + numq.y * x.kd1) * sq, (numq.y * A1 - numq.x * x.kd1) * sq);
+      if constexpr (MODE == 2) {                           // rows outside the box are not needed: zero
+        const int iw = wrap_half(j + ko * T, N);
+        if (iw < x.ylo || iw > x.yhi) val = make_float2(0.f, 0.f);
       }
       d[(FIRST ? ko : ko * T) * es] = val;
     });
-    j += qNT; l += rNT;
-    if (l >= N) { l -= N; ++j; }
+    j += qNT; li += rNT;
+    if (li >= nl) { li -= nl; ++j; }
+  }
+  if constexpr (MODE == 2) {
+    // columns outside the bounding box: zero as well (the next O * P and its row transforms read zeros there)
+    const int ncz = N - nl, lane = tid & 31;
+    for (int row = tid >> 5; row < N; row += NT / 32)
+      for (int cz = lane; cz < ncz; cz += 32) {
+        int c = l0 + nl + cz;
+        if (c < 0) c += N;
+        else if (c >= N) c -= N;
+        dst[row * es + c] = make_float2(0.f, 0.f);
+      }
   }
   __syncthreads();
 }
 
-// R1 * R2 == Np: two-stage plan with compile-time radices (M and C fused into the column stages, the pupil increment Q
-// shares the field buffer); R1 == 0: radices from p.rad at run time, every step its own pass.
+// R1 * R2 == Np: two-stage plan with compile-time radices (M fused into its column stage, pointwise passes and the
+// row / column transforms pruned to the bounding box of the pupil support, the pupil increment Q shares the field buffer); R1 == 0: radices from p.rad at run time, every step its own pass.
 template <int NT, int R1, int R2>
 __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_constant__ GeneralFusedParams p) {
   constexpr bool PLAN = R1 > 0;
@@ -159,24 +151,26 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
   const float kd1 = p.kappa * p.delta1, kd2 = p.kappa * p.delta2;
   const float epsr = p.eps * (float)NN, epsi = p.kappa * epsr;
 
+  // bounding box of the pupil support (PLAN: P, Q and the object increment are zero outside it and never touched)
+  const int NRb = p.yhi - p.ylo + 1, NCb = p.xhi - p.xlo + 1, nbox = NRb * NCb;
   // element index stepping t -> (i, j) = (t / N, t % N) without dividing inside the loops
   const int qNT = NT / N, rNT = NT % N, ti0 = tid / N, tj0 = tid % N;
   auto step = [&](int& q, int& r) { q += qNT; r += rNT; if (r >= N) { r -= N; ++q; } };
 
   // per-lane partial maximum of the 16x16 cell (a, b) from the spectrum, one warp: lanes = 2 rows x 16 columns per load
   auto cell_part = [&](int a, int b) -> float {
-    const int c = (b << 4) + (lane & 15);
-    float m = 0.f;
-    if (c < L) {
+    // cells cut by the spectrum border: indices clamped (a pixel counted twice does not change the maximum), so the
+    // eight loads are unconditional and in flight together
+    const int c = min((b << 4) + (lane & 15), L - 1);
+    float2 o[8];
 #pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = (a << 4) + 2 * rr + (lane >> 4);
-        if (r < L) {
-          const float2 o = __ldcg(objFc + (size_t)r * L + c);
-          m = fmaxf(m, fmaf(o.x, o.x, o.y * o.y));
-        }
-      }
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = min((a << 4) + 2 * rr + (lane >> 4), L - 1);
+      o[rr] = __ldcg(objFc + (size_t)r * L + c);
     }
+    float m = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) m = fmaxf(m, fmaf(o[rr].x, o[rr].x, o[rr].y * o[rr].y));
     return m;
   };
   auto grid_max = [&]() -> float {                   // scan of U; all threads return the maximum (two barriers)
@@ -226,6 +220,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
 
   // ---- prologue: twiddles, the grid of cell maxima, max|objF|^2 ----
   for (int t = tid; t < N; t += NT) tws[t] = p.tw[t];
+  if constexpr (PLAN)
+    for (int t = tid; t < N * PITCH; t += NT) bufF[t] = make_float2(0.f, 0.f);
   for (int t = warp; t < p.cgr * p.cgc; t += 2 * NW) {           // two cells per warp in flight
     const int t1 = t + NW;
     const float m0 = cell_part(t / p.cgc, t % p.cgc);
@@ -238,6 +234,12 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
   bool pending = false;                                       // Q of the previous update not yet added to P
 
   int slot = p.slot_begin % p.n_leds;
+#ifdef FPM_STAGE_TIMING
+  long long tacc_[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tacc_[k] = 0;
+  long long tprev_ = clock64();
+#endif
   for (int u = 0; u < p.n_updates; ++u) {
     const short2 cr = p.crop[slot];
     float2* O = objFc + (size_t)(cr.y + H) * L + (cr.x + H);           // window origin: wrapped indices -H .. H-1
@@ -247,6 +249,39 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
     {
       const float inv_omax = pending ? rsqrt_fast(omax2) : 0.f;
       float pm2 = 0.f;
+      if constexpr (PLAN) {
+        constexpr int UA = 8;
+        const int qb = NT / NCb, rb = NT % NCb;
+        int bi = tid / NCb, bj = tid % NCb;
+        for (int t = tid; t < nbox; t += UA * NT) {             // UA elements in flight: their global loads are issued together
+          float2 pv[UA], ov[UA];
+          int fo[UA], pe[UA];
+#pragma unroll
+          for (int k = 0; k < UA; ++k) {
+            const bool in = t + k * NT < nbox;                  // past the end: the box's first element, loaded and dropped
+            const int iw = p.ylo + (in ? bi : 0), jw = p.xlo + (in ? bj : 0);
+            const int i = iw < 0 ? iw + N : iw, j = jw < 0 ? jw + N : jw;
+            fo[k] = i * PITCH + j;
+            pe[k] = i * N + j;
+            pv[k] = P[pe[k]];
+            ov[k] = O[iw * L + jw];
+            bi += qb; bj += rb;
+            if (bj >= NCb) { bj -= NCb; ++bi; }
+          }
+#pragma unroll
+          for (int k = 0; k < UA; ++k)
+            if (t + k * NT < nbox) {
+              if (pending) {
+                const float2 qv = bufF[fo[k]];
+                pv[k].x = fmaf(qv.x, inv_omax, pv[k].x);
+                pv[k].y = fmaf(qv.y, inv_omax, pv[k].y);
+                P[pe[k]] = pv[k];
+              }
+              pm2 = fmaxf(pm2, fmaf(pv[k].x, pv[k].x, pv[k].y * pv[k].y));
+              bufF[fo[k]] = cmul(ov[k], pv[k]);
+            }
+        }
+      } else {
       int i = ti0, j = tj0;
       constexpr int UA = PLAN ? 8 : UN;
       for (int t = tid; t < NN; t += UA * NT) {               // UA elements in flight: their global loads are issued together
@@ -271,26 +306,71 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
             bufF[fo[k]] = cmul(ov[k], pv[k]);
           }
       }
+      }
       pm2 = warp_max(pm2);
       if (lane == 0) red[warp] = pm2;
+      FPM_TICK(11);
     }
     __syncthreads();
     const float inv_pmax = rsqrt_fast(warp_max(red[lane % NW]));
+    FPM_TICK(1);
 
     if constexpr (PLAN) {
       StageExtra x;
-      x.inv_i = stack + (size_t)slot * NN; x.O = O; x.P = P; x.support = p.support; x.L = L;
-      x.epsr = epsr; x.epsi = epsi; x.delta1 = p.delta1; x.delta2 = p.delta2; x.kd1 = kd1; x.kd2 = kd2; x.inv_pmax = inv_pmax;
-      // ---- I: inverse transform, rows then columns; M fused into the last column stage ----
-      plan_stage<NT, R1, true, true, 0>(bufF, bufQ, tws, N, 1, PITCH, tid, x);
-      plan_stage<NT, R2, true, false, 0>(bufQ, bufF, tws, N, 1, PITCH, tid, x);
-      plan_stage<NT, R1, true, true, 0>(bufF, bufQ, tws, N, PITCH, 1, tid, x);
-      plan_stage<NT, R2, true, false, 1>(bufQ, bufF, tws, N, PITCH, 1, tid, x);
-      // ---- F: forward transform; C fused into the last column stage (Q replaces Phi' in bufF) ----
-      plan_stage<NT, R1, false, true, 0>(bufF, bufQ, tws, N, 1, PITCH, tid, x);
-      plan_stage<NT, R2, false, false, 0>(bufQ, bufF, tws, N, 1, PITCH, tid, x);
-      plan_stage<NT, R1, false, true, 0>(bufF, bufQ, tws, N, PITCH, 1, tid, x);
-      plan_stage<NT, R2, false, false, 2>(bufQ, bufF, tws, N, PITCH, 1, tid, x);
+      x.inv_i = stack + (size_t)slot * NN; x.ylo = p.ylo; x.yhi = p.yhi; x.epsr = epsr; x.epsi = epsi;
+      // ---- I: inverse transform, rows (only those of the bounding box: the others are zero and stay zero) then
+      //         columns; M fused into the last column stage ----
+      plan_stage<NT, R1, true, true, 0>(bufF, bufQ, tws, N, 1, PITCH, tid, p.ylo, NRb, x); FPM_TICK(2);
+      plan_stage<NT, R2, true, false, 0>(bufQ, bufF, tws, N, 1, PITCH, tid, p.ylo, NRb, x); FPM_TICK(3);
+      plan_stage<NT, R1, true, true, 0>(bufF, bufQ, tws, N, PITCH, 1, tid, 0, N, x); FPM_TICK(4);
+      plan_stage<NT, R2, true, false, 1>(bufQ, bufF, tws, N, PITCH, 1, tid, 0, N, x); FPM_TICK(5);
+      // ---- F: forward transform, rows then the columns of the bounding box; C fused into the last column stage
+      //         (Q replaces Phi' in bufF, zero outside the box) ----
+      plan_stage<NT, R1, false, true, 0>(bufF, bufQ, tws, N, 1, PITCH, tid, 0, N, x); FPM_TICK(6);
+      plan_stage<NT, R2, false, false, 0>(bufQ, bufF, tws, N, 1, PITCH, tid, 0, N, x); FPM_TICK(7);
+      plan_stage<NT, R1, false, true, 0>(bufF, bufQ, tws, N, PITCH, 1, tid, p.xlo, NCb, x); FPM_TICK(8);
+      plan_stage<NT, R2, false, false, 2>(bufQ, bufF, tws, N, PITCH, 1, tid, p.xlo, NCb, x); FPM_TICK(9);
+      // ---- C: object update (old pupil) written to the spectrum, Q from the old window in place of Phi' ----
+      {
+        constexpr int UC = 4;
+        const int qb = NT / NCb, rb = NT % NCb;
+        int bi = tid / NCb, bj = tid % NCb;
+        for (int t = tid; t < nbox; t += UC * NT) {
+          float2 Ovs[UC], Pvs[UC];
+          float sup[UC];
+          int fo[UC], oo[UC];
+#pragma unroll
+          for (int k = 0; k < UC; ++k) {
+            const bool in = t + k * NT < nbox;
+            const int iw = p.ylo + (in ? bi : 0), jw = p.xlo + (in ? bj : 0);
+            const int i = iw < 0 ? iw + N : iw, j = jw < 0 ? jw + N : jw;
+            fo[k] = i * PITCH + j;
+            oo[k] = iw * L + jw;
+            Ovs[k] = O[oo[k]];
+            Pvs[k] = P[i * N + j];
+            sup[k] = __ldg(p.support + i * N + j);
+            bi += qb; bj += rb;
+            if (bj >= NCb) { bj -= NCb; ++bi; }
+          }
+#pragma unroll
+          for (int k = 0; k < UC; ++k)
+            if (t + k * NT < nbox) {
+              const float2 Ov = Ovs[k], Pv = Pvs[k];
+              const float2 d = csub(bufF[fo[k]], cmul(Ov, Pv));
+              const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
+              const float2 num = cmulc(d, Pv);
+              const float A = pa2 + p.delta2;
+              const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
+              O[oo[k]] = make_float2(Ov.x + (num.x * A + num.y * kd2) * sc, Ov.y + (num.y * A - num.x * kd2) * sc);
+              const float oa2 = fmaf(Ov.x, Ov.x, Ov.y * Ov.y);
+              const float2 numq = cmulc(d, Ov);
+              const float A1 = oa2 + p.delta1;
+              const float sq = __fdividef(sqrt_fast(oa2) * sup[k], fmaf(A1, A1, kd1 * kd1));
+              bufF[fo[k]] = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
+            }
+        }
+      }
+      FPM_TICK(14);
     } else {
       // ---- I: inverse transform, rows then columns (2 * nrad stages: the result is back in bufF) ----
       lines_fft(std::true_type{}, fa, fb, 1, PITCH);
@@ -362,7 +442,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
 
     // ---- D: touched cells, max|objF|^2 ----
     {
-      const int a0 = cr.y >> 4, a1 = (cr.y + N - 1) >> 4, b0 = cr.x >> 4, b1 = (cr.x + N - 1) >> 4;
+      // rows / columns of the spectrum this update wrote: the window (PLAN: its part inside the bounding box)
+      const int wy0 = PLAN ? cr.y + H + p.ylo : cr.y, wy1 = PLAN ? cr.y + H + p.yhi : cr.y + N - 1;
+      const int wx0 = PLAN ? cr.x + H + p.xlo : cr.x, wx1 = PLAN ? cr.x + H + p.xhi : cr.x + N - 1;
+      const int a0 = wy0 >> 4, a1 = wy1 >> 4, b0 = wx0 >> 4, b1 = wx1 >> 4;
       const int nb = b1 - b0 + 1, nc = (a1 - a0 + 1) * nb;
       for (int t = warp; t < nc; t += 2 * NW) {                // two cells per warp in flight
         const int t1 = t + NW;
@@ -373,22 +456,43 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
         if (lane == 0) { U[ca * p.cgc + cb] = r0; if (t1 < nc) U[ca1 * p.cgc + cb1] = r1; }
       }
     }
+    FPM_TICK(12);
     __syncthreads();
+    FPM_TICK(13);
     omax2 = grid_max();
     pending = true;
     if (++slot == p.n_leds) slot = 0;
+    FPM_TICK(10);
   }
+#ifdef FPM_STAGE_TIMING
+  if (tid == 0 && blockIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) p.stage_clk[k] += tacc_[k];
+  }
+#endif
 
   // ---- epilogue: the last pupil update ----
   if (pending) {
     const float inv_omax = rsqrt_fast(omax2);
-    int i = ti0, j = tj0;
-    for (int t = tid; t < NN; t += NT, step(i, j)) {
-      float2 pv = P[t];
-      const float2 qv = qbuf[i * PITCH + j];
-      pv.x = fmaf(qv.x, inv_omax, pv.x);
-      pv.y = fmaf(qv.y, inv_omax, pv.y);
-      P[t] = pv;
+    if constexpr (PLAN) {
+      for (int t = tid; t < nbox; t += NT) {
+        const int iw = p.ylo + t / NCb, jw = p.xlo + t % NCb;
+        const int i = iw < 0 ? iw + N : iw, j = jw < 0 ? jw + N : jw;
+        float2 pv = P[i * N + j];
+        const float2 qv = bufF[i * PITCH + j];
+        pv.x = fmaf(qv.x, inv_omax, pv.x);
+        pv.y = fmaf(qv.y, inv_omax, pv.y);
+        P[i * N + j] = pv;
+      }
+    } else {
+      int i = ti0, j = tj0;
+      for (int t = tid; t < NN; t += NT, step(i, j)) {
+        float2 pv = P[t];
+        const float2 qv = bufQ[i * PITCH + j];
+        pv.x = fmaf(qv.x, inv_omax, pv.x);
+        pv.y = fmaf(qv.y, inv_omax, pv.y);
+        P[t] = pv;
+      }
     }
   }
 }

@@ -328,8 +328,8 @@ static int select_variant(fpmb200_ctx* c) {
     if (c->gfused) {
       c->smem_bytes = general_fused_smem_bytes(N, c->cgr, c->cgc);
       const int plan = general_fused_plan(N);
-      char radices[48];
-      if (plan) snprintf(radices, sizeof radices, "radix %d x %d in registers, M and C fused into the column stages", plan / 100, plan % 100);
+      char radices[64];
+      if (plan) snprintf(radices, sizeof radices, "radix %d x %d in registers, pruned to the pupil box", plan / 100, plan % 100);
       else snprintf(radices, sizeof radices, "run-time radices, %d stages", fp.nrad);
       snprintf(c->variant, sizeof c->variant,
                "general path, fused: fpm_update_general_kernel (one CTA per tile, field in shared memory, Stockham %s) "
@@ -579,11 +579,16 @@ static int run_updates_general_fused(fpmb200_ctx* c, int first, int n, int slot_
   p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop; p.tw = c->twN;
   p.N = c->N; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first; p.slot_begin = slot_begin; p.n_updates = n_updates;
   p.cgr = c->cgr; p.cgc = c->cgc;
+  p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi;
   p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
   LineFFTParams fp;
   factorize(c->N, fp);
   p.nrad = fp.nrad;
   for (int s = 0; s < fp.nrad; ++s) p.rad[s] = fp.rad[s];
+#ifdef FPM_STAGE_TIMING
+  if (!c->stage_clk) { CK(cudaMalloc(&c->stage_clk, 16 * sizeof(long long))); CK(cudaMemset(c->stage_clk, 0, 16 * sizeof(long long))); }
+  p.stage_clk = c->stage_clk;
+#endif
   // two-stage plans with compile-time radices for the sizes of the shipped JSONs (and their neighbours); other sizes
   // take the radices at run time
   void (*k)(const GeneralFusedParams) = fpm_update_general_kernel<512, 0, 0>;

@@ -20,6 +20,9 @@ for name in names:
         n_upd = 2 * len(c.cx)
         v = np.array(list(buf), dtype=np.float64) / n_upd
         labels = ["-", "S1 colA(inv)+O*P", "S2 colB(inv)", "S3 rowA(inv)", "S4 rowB+amp+rowB'", "S5 rowA'", "S6 colB'", "S7 colA'", "C2 object update", "D max|objF|", "E pupil+next window"]
+        if "general path, fused" in ctx.variant:
+            labels = ["-", "A P+=Q, O*P, max|P|", "I row stage 1", "I row stage 2", "I col stage 1", "I col stage 2 + M", "F row stage 1",
+                      "F row stage 2", "F col stage 1", "F col stage 2 + C", "D max|objF|"]
         print(name, "tiles", n_tiles, ctx.variant)
         for k in range(1, 11):
             print("   %-20s %8.0f cyc  %5.1f%%" % (labels[k], v[k], 100 * v[k] / v[1:16].sum()))
