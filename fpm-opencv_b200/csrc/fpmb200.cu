@@ -558,6 +558,12 @@ static void drop_graphs(fpmb200_ctx* c) {
   c->iter_graphs.clear();
 }
 
+// threads per CTA of fpm_update_general_kernel
+#ifndef FPM_GEN_NT
+#define FPM_GEN_NT 512
+#endif
+static constexpr int GEN_NT = FPM_GEN_NT;
+
 // R1 * 100 + R2 of the compiled two-stage plan for Np, 0 if there is none
 static int general_fused_plan(int N) {
   const char* e = getenv("FPMB200_GENERAL_PLAN");
@@ -591,18 +597,18 @@ static int run_updates_general_fused(fpmb200_ctx* c, int first, int n, int slot_
 #endif
   // two-stage plans with compile-time radices for the sizes of the shipped JSONs (and their neighbours); other sizes
   // take the radices at run time
-  void (*k)(const GeneralFusedParams) = fpm_update_general_kernel<512, 0, 0>;
+  void (*k)(const GeneralFusedParams) = fpm_update_general_kernel<GEN_NT, 0, 0>;
   switch (general_fused_plan(c->N)) {
-    case 1009: k = fpm_update_general_kernel<512, 10, 9>; break;
-    case 1010: k = fpm_update_general_kernel<512, 10, 10>; break;
-    case 1008: k = fpm_update_general_kernel<512, 10, 8>; break;
-    case 908: k = fpm_update_general_kernel<512, 9, 8>; break;
-    case 1606: k = fpm_update_general_kernel<512, 16, 6>; break;
-    case 1006: k = fpm_update_general_kernel<512, 10, 6>; break;
+    case 1009: k = fpm_update_general_kernel<GEN_NT, 10, 9>; break;
+    case 1010: k = fpm_update_general_kernel<GEN_NT, 10, 10>; break;
+    case 1008: k = fpm_update_general_kernel<GEN_NT, 10, 8>; break;
+    case 908: k = fpm_update_general_kernel<GEN_NT, 9, 8>; break;
+    case 1606: k = fpm_update_general_kernel<GEN_NT, 16, 6>; break;
+    case 1006: k = fpm_update_general_kernel<GEN_NT, 10, 6>; break;
     default: break;
   }
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-  k<<<n, 512, c->smem_bytes, st>>>(p);
+  k<<<n, GEN_NT, c->smem_bytes, st>>>(p);
   c->launches++;
   CK(cudaGetLastError());
   return FPMB200_OK;

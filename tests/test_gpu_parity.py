@@ -339,13 +339,17 @@ def test_dense_support_uses_general_path():
         ctx.close()
 
 
-def test_asymmetric_support_bbox():
-    """An off-centre elliptical support exercises the wrapped bbox arithmetic."""
-    c = T.Case("cfg1_mono_np64", 4, 16)
+@pytest.mark.parametrize("name,ell", [("cfg1_mono_np64", (3, 14.0, -5, 9.0)), ("cfg7_mono_np90", (3, 14.0, -5, 9.0)),
+                                      ("cfg7_mono_np90", (20, 9.0, 12, 6.0)), ("cfg8_cellScope_np100", (-24, 11.0, 0, 30.0))])
+def test_asymmetric_support_bbox(name, ell):
+    """An off-centre elliptical support exercises the wrapped bbox arithmetic (fused power-of-two kernel and the
+    fused general kernel; boxes that straddle the origin, lie on one side of it, or span all rows)."""
+    c = T.Case(name, 4, 16)
     N = c.N
     y, x = np.mgrid[0:N, 0:N]
     yw, xw = np.where(y < N // 2, y, y - N), np.where(x < N // 2, x, x - N)
-    S = ((((xw - 3) / 14.0) ** 2 + ((yw + 5) / 9.0) ** 2) <= 1).astype(np.float32)
+    x0, ax, y0, ay = ell
+    S = ((((xw - x0) / ax) ** 2 + ((yw - y0) / ay) ** 2) <= 1).astype(np.float32)
     ctx = c.make_ctx(support=S)
     st = orc.State(orc.init_state(c.stack, c.L, c.r).objFc, S.astype(np.complex128), S.astype(np.float64))
     ctx.upload_state(0, T.corner(st.objFc), st.P)
@@ -357,9 +361,10 @@ def test_asymmetric_support_bbox():
     ctx.close()
 
 
-def test_windows_touching_the_spectrum_border():
+@pytest.mark.parametrize("name", ["cfg1_mono_np64", "cfg7_mono_np90"])
+def test_windows_touching_the_spectrum_border(name):
     """Crop origins 0 and Nlarge-Np (the legal extremes, fpmMain.cpp:157-165)."""
-    c = T.Case("cfg1_mono_np64", 5, 8)
+    c = T.Case(name, 5, 8)
     c.cx = np.array([0, c.L - c.N, 0, c.L - c.N, 96, 7, c.L - c.N - 1, 1], np.int16)
     c.cy = np.array([0, 0, c.L - c.N, c.L - c.N, 96, c.L - c.N - 3, 5, 1], np.int16)
     ctx = c.make_ctx()

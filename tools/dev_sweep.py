@@ -3,6 +3,9 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "fpm-opencv_b200"), os.path.join(ROOT, "tests")]
 import torch
+import fpmb200
+if os.environ.get("FPM_LIB"):
+    fpmb200.lib_path = lambda: os.path.join(fpmb200.LIB_DIR, os.environ["FPM_LIB"])
 import fpm_testlib as T
 names = sys.argv[1:] or ["cfg1_mono_np64", "cfg2_fLEDc_np128", "cfg3b_cellScope_np64", "cfg3_cellScope_np256",
                          "cfg4_dogStomach_np128", "cfg5_cellscope2_np128", "cfg5b_cellscope2_np256"]

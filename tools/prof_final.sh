@@ -5,10 +5,12 @@ timeout 400 python bench.py > gpurun_out/r01_final_bench.json 2> gpurun_out/r01_
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r01_final_bench_reference.json 2>/dev/null
 ( FPM_TILES=148 FPM_CLUSTER=1 timeout 200 python tools/dev_stages.py cfg4_dogStomach_np128 cfg1_mono_np64 cfg5_cellscope2_np128
   FPM_TILES=1,16 timeout 200 python tools/dev_stages.py cfg5b_cellscope2_np256 cfg3_cellScope_np256
-  FPM_TILES=1 FPM_CLUSTER=4 timeout 200 python tools/dev_stages.py cfg2_fLEDc_np128 cfg5_cellscope2_np128 ) > gpurun_out/r01_final_stage_cycles.txt 2>&1
+  FPM_TILES=1 FPM_CLUSTER=4 timeout 200 python tools/dev_stages.py cfg2_fLEDc_np128 cfg5_cellscope2_np128
+  FPM_TILES=148 timeout 200 python tools/dev_stages.py cfg7_mono_np90 cfg8_cellScope_np100 ) > gpurun_out/r01_final_stage_cycles.txt 2>&1
 timeout 400 python tools/dev_sweep.py cfg1_mono_np64 cfg2_fLEDc_np128 cfg3b_cellScope_np64 cfg3_cellScope_np256 cfg4_dogStomach_np128 cfg5_cellscope2_np128 cfg5b_cellscope2_np256 cfg7_mono_np90 cfg8_cellScope_np100 cfg4s_dogStomach_np200 > gpurun_out/r01_final_config_sweep.txt 2>&1
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_final_launches.csv $CMD > gpurun_out/r01_ncu_launch.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:fpm_update_kernel -c 1 -f -o gpurun_out/r01_update_kernel $CMD > gpurun_out/r01_ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fpm_update_cluster_kernel -s 2 -c 1 -f -o gpurun_out/r01_cluster_kernel python tools/dev_sweep.py cfg5b_cellscope2_np256 > gpurun_out/r01_ncu_cluster.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fpm_update_general_kernel -s 2 -c 1 -f -o gpurun_out/r01_general_kernel python tools/dev_sweep.py cfg7_mono_np90 > gpurun_out/r01_ncu_general.log 2>&1
 ls -la gpurun_out | tail -12
