@@ -480,4 +480,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: libraries that write to file descriptor 1 on their own (NCCL prints its
+    # version banner there) are pointed at stderr for the duration of the run
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_json_fd, "w", buffering=1)
     main()

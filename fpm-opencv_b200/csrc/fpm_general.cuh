@@ -34,6 +34,7 @@ struct GeneralParams {
   float* scal;              // [n_tiles][4]: 0 = max|P|^2, 1 = max|objF|^2
   int N, L, n_leds, tile0, slot;
   int cgr, cgc;
+  int ylo, xlo, nrb, ncb;   // bounding box of the pupil support: first wrapped row / column (in [-N/2, N/2)), extent
   float delta1, delta2, eps, kappa;
   int apply;                // gen_pupil_update: 0 = only reduce max|P|^2 (start of a launch sequence)
 };
@@ -48,7 +49,9 @@ __global__ void __launch_bounds__(256) gen_window_mul(const GeneralParams p) {
   float2* F = p.field + (size_t)tile * N * N;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N * N; t += gridDim.x * blockDim.x) {
     const int i = t / N, j = t - i * N;
-    F[t] = cmul(O[wrap_half(i, N) * L + wrap_half(j, N)], P[t]);
+    const int iw = wrap_half(i, N), jw = wrap_half(j, N);
+    const bool in = (unsigned)(iw - p.ylo) < (unsigned)p.nrb && (unsigned)(jw - p.xlo) < (unsigned)p.ncb;
+    F[t] = in ? cmul(O[iw * L + jw], P[t]) : make_float2(0.f, 0.f);            // P = 0 outside the support's box
   }
 }
 
@@ -74,9 +77,10 @@ __global__ void __launch_bounds__(256) gen_object_update(const GeneralParams p) 
   float2* Q = p.q + (size_t)tile * N * N;
   const float inv_pmax = rsqrt_fast(p.scal[(size_t)tile * 4 + 0]);
   const float kd1 = p.kappa * p.delta1, kd2 = p.kappa * p.delta2;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N * N; t += gridDim.x * blockDim.x) {
-    const int i = t / N, j = t - i * N;
-    float2* op = O + wrap_half(i, N) * L + wrap_half(j, N);
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < p.nrb * p.ncb; b += gridDim.x * blockDim.x) {
+    const int bi = b / p.ncb, iw = p.ylo + bi, jw = p.xlo + (b - bi * p.ncb);          // the box: nothing changes outside
+    const int t = (iw < 0 ? iw + N : iw) * N + (jw < 0 ? jw + N : jw);
+    float2* op = O + iw * L + jw;
     const float2 Ov = *op, Pv = P[t];
     const float2 d = csub(F[t], cmul(Ov, Pv));
     const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
@@ -101,7 +105,9 @@ __global__ void __launch_bounds__(256) gen_cells_update(const GeneralParams p, i
     a = blockIdx.x / p.cgc; b = blockIdx.x % p.cgc;
   } else {
     const short2 cr = p.crop[p.slot];
-    const int a0 = cr.y >> 4, a1 = (cr.y + p.N - 1) >> 4, b0 = cr.x >> 4, b1 = (cr.x + p.N - 1) >> 4;
+    const int H = p.N / 2;                                          // the part of the window inside the box
+    const int a0 = (cr.y + H + p.ylo) >> 4, a1 = (cr.y + H + p.ylo + p.nrb - 1) >> 4;
+    const int b0 = (cr.x + H + p.xlo) >> 4, b1 = (cr.x + H + p.xlo + p.ncb - 1) >> 4;
     const int nb = b1 - b0 + 1;
     a = a0 + blockIdx.x / nb; b = b0 + blockIdx.x % nb;
     if (a > a1) return;
@@ -148,7 +154,9 @@ __global__ void __launch_bounds__(256) gen_pupil_update(const GeneralParams p) {
   const float2* Q = p.q + (size_t)tile * N * N;
   const float inv = p.apply ? rsqrt_fast(p.scal[(size_t)tile * 4 + 1]) : 0.f;
   float m = 0.f;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N * N; t += gridDim.x * blockDim.x) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < p.nrb * p.ncb; b += gridDim.x * blockDim.x) {
+    const int bi = b / p.ncb, iw = p.ylo + bi, jw = p.xlo + (b - bi * p.ncb);
+    const int t = (iw < 0 ? iw + N : iw) * N + (jw < 0 ? jw + N : jw);
     float2 v = P[t];
     if (p.apply) {
       const float2 qv = Q[t];

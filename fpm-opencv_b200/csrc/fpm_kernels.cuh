@@ -26,6 +26,7 @@ struct LineFFTParams {
   long long batch_stride;   // elements between images
   int n;                    // transform length
   int n_lines;              // lines per image
+  int line_first, n_sel;    // the lines transformed: line_first, line_first+1, ... (mod n_lines), n_sel of them
   long long elem_stride;    // elements between consecutive samples of a line
   long long line_stride;    // elements between consecutive lines
   int nrad;                 // number of stages
@@ -46,7 +47,11 @@ __global__ void __launch_bounds__(256) line_fft_kernel(const __grid_constant__ L
     int l, k;
     if (p.line_stride == 1) { l = t % LINES; k = t / LINES; } else { k = t % n; l = t / n; }
     float2 v = make_float2(0.f, 0.f);
-    if (line0 + l < p.n_lines) v = img[(size_t)(line0 + l) * p.line_stride + (size_t)k * p.elem_stride];
+    if (line0 + l < p.n_sel) {
+      int ln = p.line_first + line0 + l;
+      if (ln >= p.n_lines) ln -= p.n_lines;
+      v = img[(size_t)ln * p.line_stride + (size_t)k * p.elem_stride];
+    }
     bufA[l * n + k] = v;
   }
   __syncthreads();
@@ -86,9 +91,11 @@ __global__ void __launch_bounds__(256) line_fft_kernel(const __grid_constant__ L
   for (int t = threadIdx.x; t < LINES * n; t += blockDim.x) {
     int l, k;
     if (p.line_stride == 1) { l = t % LINES; k = t / LINES; } else { k = t % n; l = t / n; }
-    if (line0 + l < p.n_lines) {
+    if (line0 + l < p.n_sel) {
+      int ln = p.line_first + line0 + l;
+      if (ln >= p.n_lines) ln -= p.n_lines;
       float2 v = src[l * n + k];
-      img[(size_t)(line0 + l) * p.line_stride + (size_t)k * p.elem_stride] = make_float2(v.x * p.scale, v.y * p.scale);
+      img[(size_t)ln * p.line_stride + (size_t)k * p.elem_stride] = make_float2(v.x * p.scale, v.y * p.scale);
     }
   }
 }

@@ -469,10 +469,16 @@ static void factorize(int n, LineFFTParams& p) {
   while (n % 5 == 0) { p.rad[p.nrad++] = 5; n /= 5; }
 }
 
+// 2-D transform of `batch` n x n images in place: rows, then columns.  row0 / nrows (col0 / ncols) restrict the row
+// (column) pass to a wrapped range of lines: rows known to be zero need no transform, columns whose result is not
+// used need none either (the update's O * P is zero outside the bounding box of the pupil support, and only the box
+// of Phi' is consumed).  nrows = ncols = n: the full transform.
 template <bool INV>
 static int fft2d(fpmb200_ctx* c, float2* data, int n, const float2* tw, int batch, long long batch_stride, float scale,
-                 cudaStream_t st) {
+                 cudaStream_t st, int row0 = 0, int nrows = -1, int col0 = 0, int ncols = -1) {
   constexpr int LINES = 4;
+  if (nrows < 0) nrows = n;
+  if (ncols < 0) ncols = n;
   LineFFTParams p;
   memset(&p, 0, sizeof p);
   p.data = data; p.tw = tw; p.batch_stride = batch_stride; p.n = n; p.n_lines = n;
@@ -481,11 +487,12 @@ static int fft2d(fpmb200_ctx* c, float2* data, int n, const float2* tw, int batc
   if (smem > (size_t)c->max_smem_optin) return fail(FPMB200_ERR_ARG, "line FFT of length %d needs %zu B shared memory", n, smem);
   auto kern = line_fft_kernel<INV, LINES>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((n + LINES - 1) / LINES, batch);
   p.elem_stride = 1; p.line_stride = n; p.scale = 1.f;            // rows
-  kern<<<grid, 256, smem, st>>>(p);
+  p.line_first = row0; p.n_sel = nrows;
+  kern<<<dim3((nrows + LINES - 1) / LINES, batch), 256, smem, st>>>(p);
   p.elem_stride = n; p.line_stride = 1; p.scale = scale;          // columns
-  kern<<<grid, 256, smem, st>>>(p);
+  p.line_first = col0; p.n_sel = ncols;
+  kern<<<dim3((ncols + LINES - 1) / LINES, batch), 256, smem, st>>>(p);
   c->launches += 2;
   CK(cudaGetLastError());
   return FPMB200_OK;
@@ -547,10 +554,6 @@ static int launch_cluster(fpmb200_ctx* c, const UpdateParams& p, int n_tiles, cu
   c->launches++;
   return FPMB200_OK;
 }
-
-template <bool INV>
-static int fft2d(fpmb200_ctx* c, float2* data, int n, const float2* tw, int batch, long long batch_stride, float scale,
-                 cudaStream_t st);
 
 // The unfused path (csrc/fpm_general.cuh): 11 launches per update, every launch covers tiles [first, first+n).
 static void drop_graphs(fpmb200_ctx* c) {
@@ -623,16 +626,21 @@ static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin,
   p.field = c->gfield; p.q = c->gq; p.cells = c->gcells; p.scal = c->gscal;
   p.N = N; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first; p.cgr = c->cgr; p.cgc = c->cgc;
   p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
+  // bounding box of the pupil support: P, Q and the object increment vanish outside it
+  p.ylo = c->ylo; p.xlo = c->xlo; p.nrb = c->yhi - c->ylo + 1; p.ncb = c->xhi - c->xlo + 1;
+  const int row0 = c->ylo < 0 ? c->ylo + N : c->ylo, col0 = c->xlo < 0 ? c->xlo + N : c->xlo;
   const int bx = (N * N + 255) / 256 < 64 ? (N * N + 255) / 256 : 64;
   const dim3 ge(bx, n);
-  const int tc = (N + 15) / 16 + 1;                              // cells a window can touch per dimension
+  const int nbx = (p.nrb * p.ncb + 255) / 256 < 64 ? (p.nrb * p.ncb + 255) / 256 : 64;
+  const dim3 gb(nbx, n);                                          // kernels over the box
+  const int tc = (p.nrb > p.ncb ? p.nrb : p.ncb) / 16 + 2;       // cells the box of a window can touch per dimension
   float2* fld = c->gfield + (size_t)first * N * N;
   // state the loop carries in scal: max|P|^2 of the current pupil; the cell grid of the current spectrum
   p.apply = 1; p.slot = 0;
   gen_cells_update<<<dim3(c->cgr * c->cgc, n), 256, 0, st>>>(p, 1);
   gen_cells_max<<<n, 256, 0, st>>>(p);
   p.apply = 0;
-  gen_pupil_update<<<ge, 256, 0, st>>>(p);
+  gen_pupil_update<<<gb, 256, 0, st>>>(p);
   c->launches += 3;
   p.apply = 1;
   auto enqueue = [&](int u0, int u1) -> int {
@@ -640,13 +648,14 @@ static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin,
     for (int u = u0; u < u1; ++u) {
       p.slot = (slot_begin + u) % c->n_leds;
       gen_window_mul<<<ge, 256, 0, st>>>(p);
-      if ((rc = fft2d<true>(c, fld, N, c->twN, n, (long long)N * N, 1.f / ((float)N * (float)N), st))) return rc;
+      // inverse: only the box's rows are non-zero; forward: only the box's columns are consumed
+      if ((rc = fft2d<true>(c, fld, N, c->twN, n, (long long)N * N, 1.f / ((float)N * (float)N), st, row0, p.nrb, 0, N))) return rc;
       gen_amplitude<<<ge, 256, 0, st>>>(p);
-      if ((rc = fft2d<false>(c, fld, N, c->twN, n, (long long)N * N, 1.f, st))) return rc;
-      gen_object_update<<<ge, 256, 0, st>>>(p);
+      if ((rc = fft2d<false>(c, fld, N, c->twN, n, (long long)N * N, 1.f, st, 0, N, col0, p.ncb))) return rc;
+      gen_object_update<<<gb, 256, 0, st>>>(p);
       gen_cells_update<<<dim3(tc * tc, n), 256, 0, st>>>(p, 0);
       gen_cells_max<<<n, 256, 0, st>>>(p);
-      gen_pupil_update<<<ge, 256, 0, st>>>(p);
+      gen_pupil_update<<<gb, 256, 0, st>>>(p);
       c->launches += 10;
     }
     return FPMB200_OK;

@@ -339,11 +339,15 @@ def test_dense_support_uses_general_path():
         ctx.close()
 
 
-@pytest.mark.parametrize("name,ell", [("cfg1_mono_np64", (3, 14.0, -5, 9.0)), ("cfg7_mono_np90", (3, 14.0, -5, 9.0)),
-                                      ("cfg7_mono_np90", (20, 9.0, 12, 6.0)), ("cfg8_cellScope_np100", (-24, 11.0, 0, 30.0))])
-def test_asymmetric_support_bbox(name, ell):
-    """An off-centre elliptical support exercises the wrapped bbox arithmetic (fused power-of-two kernel and the
-    fused general kernel; boxes that straddle the origin, lie on one side of it, or span all rows)."""
+@pytest.mark.parametrize("name,ell,unfused", [("cfg1_mono_np64", (3, 14.0, -5, 9.0), 0), ("cfg7_mono_np90", (3, 14.0, -5, 9.0), 0),
+                                              ("cfg7_mono_np90", (20, 9.0, 12, 6.0), 0), ("cfg8_cellScope_np100", (-24, 11.0, 0, 30.0), 0),
+                                              ("cfg7_mono_np90", (3, 14.0, -5, 9.0), 1), ("cfg7_mono_np90", (20, 9.0, 12, 6.0), 1),
+                                              ("cfg4s_dogStomach_np200", (-60, 25.0, 33, 40.0), 0)])
+def test_asymmetric_support_bbox(name, ell, unfused, monkeypatch):
+    """An off-centre elliptical support exercises the wrapped bbox arithmetic (fused power-of-two kernel, the fused
+    general kernel and the unfused general path; boxes that straddle the origin or lie on one side of it)."""
+    if unfused:
+        monkeypatch.setenv("FPMB200_GENERAL_UNFUSED", "1")
     c = T.Case(name, 4, 16)
     N = c.N
     y, x = np.mgrid[0:N, 0:N]
