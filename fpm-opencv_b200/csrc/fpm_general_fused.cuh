@@ -6,18 +6,22 @@
 //
 //   A   pending pupil update P += Q / max|objF| (of the previous LED, fpmMain.cpp:470-475) fused with the window fetch
 //       and Phi = O * P (:358-364); max|P|^2 reduced on the way (:415)
-//   I   inverse 2-D transform, mixed-radix (4,2,3,5) Stockham stages between two shared-memory copies of the field,
-//       rows then columns, unscaled (the 1/Np^2 of ifft2 cancels in psi/|psi+eps|; eps is scaled instead)   (:365)
+//   I   inverse 2-D transform, Stockham stages between two shared-memory copies of the field, rows then columns,
+//       unscaled (the 1/Np^2 of ifft2 cancels in psi/|psi+eps|; eps is scaled instead).  Np = R1 * R2 with both
+//       radices compiled in (plan_stage: 90 = 10 x 9, 100 = 10 x 10 ...), else radices 4,2,3,5 at run time    (:365)
 //   M   psi' = psi * rsqrt(|psi+eps|^2 * (1/I))                                                             (:378-393)
 //   F   forward 2-D transform                                                                                (:394)
-//   C   dPhi = Phi' - O P;  O += dPhi |P| P* / D_O written to the spectrum;  Q = dPhi |O| O* / D_P * S kept in the
-//       second field buffer (it is the transform's scratch and free between F and the next I)      (:406-447,459-472)
+//   C   dPhi = Phi' - O P;  O += dPhi |P| P* / D_O written to the spectrum;  Q = dPhi |O| O* / D_P * S kept on chip
+//       (plans: in place of Phi' in the field buffer; run-time radices: in the scratch buffer)     (:406-447,459-472)
 //   D   exact max|objF|: the 16x16-pixel cells of the grid of cell maxima that the window touches are rebuilt from
 //       the spectrum, the grid (shared memory) is scanned                                                  (:460,467)
 //
 // The field never leaves shared memory; lanes run over LINES in every transform stage (rows: odd pitch, columns:
 // adjacent addresses), so all 64-bit accesses of a half-warp fall into distinct bank pairs for any Np, and the
 // butterfly index -- hence the twiddle -- is uniform over (nearly) the whole warp.
+// With a compiled plan everything is pruned to the bounding box of the pupil support (P, Q and the object increment
+// vanish outside it): A, C and D touch the box only, the inverse row stages run the box's rows (the other rows of
+// O * P are zero), the forward column stages the box's columns.
 // Same arithmetic and conventions as fpm_general.cuh (the unfused path, which stays for tiles too large for this
 // kernel, e.g. cropSizeX = 200).
 #pragma once
@@ -63,8 +67,8 @@ struct StageExtra {
 // twiddles, outputs contiguous (j*R + k); otherwise radix R2, inputs twiddled by W_N^(r*j), outputs at j + k*R1.
 // Work item t = j * nl + li over the nl lines l0 .. l0+nl-1 (wrapped indices; all lines: l0 = 0, nl = N): lanes over
 // lines.  Lines outside the bounding box of the pupil support are skipped where they are known to be zero (row
-// transforms of O * P) or not needed (column transforms of Phi').  MODE 1 / 2 (column stages only: es = pitch, ls = 1, so lanes run over
-// columns and the global loads are coalesced): MODE 1 fuses M (amplitude replacement, fpmMain.cpp:378-393) into the
+// transforms of O * P) or not needed (column transforms of Phi').  MODE 1 / 2 (column stages only: es = pitch,
+// ls = 1, so lanes run over columns and the global loads are coalesced): MODE 1 fuses M (amplitude replacement, fpmMain.cpp:378-393) into the
 // stores, its 1/I operands requested before the butterflies; MODE 2 is the last forward stage: only the box of Phi' is
 // kept, everything else of dst is zeroed (C runs as its own pass over the box: fused into this stage it was
 // issue-bound on an unbalanced 1.2 rounds of work items, 13 k cycles against 2 k + 3 k separately).
@@ -72,6 +76,8 @@ template <int NT, int R, bool INV, bool FIRST, int MODE>
 __device__ __forceinline__ void plan_stage(const float2* __restrict__ src, float2* __restrict__ dst,
                                            const float2* __restrict__ tws, int N, int es, int ls, int tid,
                                            int l0, int nl, const StageExtra& x) {
+  // (padding nl to a multiple of 16 in the work-item index, so that no half-warp straddles two values of j, removes
+  // the bank-conflict replays -- 19 % of the wavefronts -- but the idle lanes cost more: -4 % measured)
   const int T = N / R, total = nl * T;
   const int qNT = NT / nl, rNT = NT % nl;
   int j = tid / nl, li = tid % nl;
@@ -127,7 +133,8 @@ __device__ __forceinline__ void plan_stage(const float2* __restrict__ src, float
 }
 
 // R1 * R2 == Np: two-stage plan with compile-time radices (M fused into its column stage, pointwise passes and the
-// row / column transforms pruned to the bounding box of the pupil support, the pupil increment Q shares the field buffer); R1 == 0: radices from p.rad at run time, every step its own pass.
+// row / column transforms pruned to the bounding box of the pupil support, the pupil increment Q shares the field
+// buffer); R1 == 0: radices from p.rad at run time, every step its own pass.
 template <int NT, int R1, int R2>
 __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_constant__ GeneralFusedParams p) {
   constexpr bool PLAN = R1 > 0;
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
             const bool in = t + k * NT < nbox;                  // past the end: the box's first element, loaded and dropped
             const int iw = p.ylo + (in ? bi : 0), jw = p.xlo + (in ? bj : 0);
             const int i = iw < 0 ? iw + N : iw, j = jw < 0 ? jw + N : jw;
-            fo[k] = i * PITCH + j;
+            fo[k] = in ? i * PITCH + j : -1;
             pe[k] = i * N + j;
             pv[k] = P[pe[k]];
             ov[k] = O[iw * L + jw];
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
           }
 #pragma unroll
           for (int k = 0; k < UA; ++k)
-            if (t + k * NT < nbox) {
+            if (fo[k] >= 0) {
               if (pending) {
                 const float2 qv = bufF[fo[k]];
                 pv[k].x = fmaf(qv.x, inv_omax, pv[k].x);
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
             const bool in = t + k * NT < nbox;
             const int iw = p.ylo + (in ? bi : 0), jw = p.xlo + (in ? bj : 0);
             const int i = iw < 0 ? iw + N : iw, j = jw < 0 ? jw + N : jw;
-            fo[k] = i * PITCH + j;
+            fo[k] = in ? i * PITCH + j : -1;
             oo[k] = iw * L + jw;
             Ovs[k] = O[oo[k]];
             Pvs[k] = P[i * N + j];
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
           }
 #pragma unroll
           for (int k = 0; k < UC; ++k)
-            if (t + k * NT < nbox) {
+            if (fo[k] >= 0) {
               const float2 Ov = Ovs[k], Pv = Pvs[k];
               const float2 d = csub(bufF[fo[k]], cmul(Ov, Pv));
               const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
   if (pending) {
     const float inv_omax = rsqrt_fast(omax2);
     if constexpr (PLAN) {
-      for (int t = tid; t < nbox; t += NT) {
+      for (int t = tid; t < NRb * NCb; t += NT) {
         const int iw = p.ylo + t / NCb, jw = p.xlo + t % NCb;
         const int i = iw < 0 ? iw + N : iw, j = jw < 0 ? jw + N : jw;
         float2 pv = P[i * N + j];

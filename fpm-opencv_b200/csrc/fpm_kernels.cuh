@@ -38,8 +38,8 @@ template <bool INV, int LINES>
 __global__ void __launch_bounds__(256) line_fft_kernel(const __grid_constant__ LineFFTParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* bufA = reinterpret_cast<float2*>(smem_raw);
-  float2* bufB = bufA + (size_t)LINES * p.n;
-  const int n = p.n;
+  const int n = p.n, np = n + 1;                // odd pitch (n is even): lanes over adjacent lines hit distinct banks
+  float2* bufB = bufA + (size_t)LINES * np;
   const int line0 = blockIdx.x * LINES;
   float2* img = p.data + (size_t)blockIdx.y * p.batch_stride;
   // load: when lines are adjacent in memory (line_stride==1) let lanes run along lines
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) line_fft_kernel(const __grid_constant__ L
       if (ln >= p.n_lines) ln -= p.n_lines;
       v = img[(size_t)ln * p.line_stride + (size_t)k * p.elem_stride];
     }
-    bufA[l * n + k] = v;
+    bufA[l * np + k] = v;
   }
   __syncthreads();
   float2* src = bufA;
@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(256) line_fft_kernel(const __grid_constant__ L
     const int tstep = n / (Ns * R);
     for (int t = threadIdx.x; t < LINES * T; t += blockDim.x) {
       const int l = t / T, j = t - l * T;
-      const float2* x = src + l * n;
-      float2* y = dst + l * n;
+      const float2* x = src + l * np;
+      float2* y = dst + l * np;
       const int k = j % Ns;
       const int j0 = (j - k) * R + k;
       float2 v[5];
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) line_fft_kernel(const __grid_constant__ L
     if (line0 + l < p.n_sel) {
       int ln = p.line_first + line0 + l;
       if (ln >= p.n_lines) ln -= p.n_lines;
-      float2 v = src[l * n + k];
+      float2 v = src[l * np + k];
       img[(size_t)ln * p.line_stride + (size_t)k * p.elem_stride] = make_float2(v.x * p.scale, v.y * p.scale);
     }
   }
