@@ -58,7 +58,6 @@ __host__ __device__ inline size_t general_fused_smem_bytes(int N, int cgr, int c
 // What the column stages with an epilogue need besides the field
 struct StageExtra {
   const float* inv_i;                 // MODE 1: 1/I of this LED, [N][N]
-  int ylo, yhi;                       // MODE 2: wrapped row range of the support's bounding box
   float epsr, epsi;                   // MODE 1
 };
 
@@ -67,15 +66,16 @@ struct StageExtra {
 // twiddles, outputs contiguous (j*R + k); otherwise radix R2, inputs twiddled by W_N^(r*j), outputs at j + k*R1.
 // Work item t = j * nl + li over the nl lines l0 .. l0+nl-1 (wrapped indices; all lines: l0 = 0, nl = N): lanes over
 // lines.  Lines outside the bounding box of the pupil support are skipped where they are known to be zero (row
-// transforms of O * P) or not needed (column transforms of Phi').  MODE 1 / 2 (column stages only: es = pitch,
-// ls = 1, so lanes run over columns and the global loads are coalesced): MODE 1 fuses M (amplitude replacement, fpmMain.cpp:378-393) into the
-// stores, its 1/I operands requested before the butterflies; MODE 2 is the last forward stage: only the box of Phi' is
-// kept, everything else of dst is zeroed (C runs as its own pass over the box: fused into this stage it was
-// issue-bound on an unbalanced 1.2 rounds of work items, 13 k cycles against 2 k + 3 k separately).
-template <int NT, int R, bool INV, bool FIRST, int MODE>
+// transforms of O * P) or not needed (column transforms of Phi'); ZIN: samples known to be zero are not read either
+// (columns outside the box in the first inverse row stage, rows outside it in the first inverse column stage), so
+// nothing outside the box ever has to be cleared.  MODE 1 (column stage: es = pitch, ls = 1, lanes run over columns
+// and the global loads are coalesced) fuses M (amplitude replacement, fpmMain.cpp:378-393) into the stores, its 1/I
+// operands requested before the butterflies.  (C runs as its own pass over the box: fused into the last forward
+// stage it was issue-bound on an unbalanced 1.2 rounds of work items, 13 k cycles against 2 k + 3 k separately.)
+template <int NT, int R, bool INV, bool FIRST, int MODE, bool ZIN = false>
 __device__ __forceinline__ void plan_stage(const float2* __restrict__ src, float2* __restrict__ dst,
                                            const float2* __restrict__ tws, int N, int es, int ls, int tid,
-                                           int l0, int nl, const StageExtra& x) {
+                                           int l0, int nl, const StageExtra& x, int z0 = 0, int nz = 0) {
   // (padding nl to a multiple of 16 in the work-item index, so that no half-warp straddles two values of j, removes
   // the bank-conflict replays -- 19 % of the wavefronts -- but the idle lanes cost more: -4 % measured)
   const int T = N / R, total = nl * T;
@@ -93,8 +93,19 @@ __device__ __forceinline__ void plan_stage(const float2* __restrict__ src, float
       });
     }
     const float2* s = src + l * ls + j * es;
+    if constexpr (ZIN) {
+      // samples whose (wrapped) index along the line lies outside [z0, z0 + nz) are zero by construction (O * P outside
+      // the box): not read -- whatever the buffer holds there is stale
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = s[r * T * es];
+      for (int r = 0; r < R; ++r) {
+        const bool in = (unsigned)(wrap_half(j + r * T, N) - z0) < (unsigned)nz;
+        v[r] = make_float2(0.f, 0.f);
+        if (in) v[r] = s[r * T * es];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = s[r * T * es];
+    }
     if constexpr (!FIRST) {
 #pragma unroll
       for (int r = 1; r < R; ++r) v[r] = twmul<INV>(v[r], tws[r * j]);
@@ -109,25 +120,10 @@ __device__ __forceinline__ void plan_stage(const float2* __restrict__ src, float
         const float sc = rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y) * ii[i]);          // sqrt(I)/|psi+eps|; I = 0 -> 0
         val = make_float2(val.x * sc, val.y * sc);
       }
-      if constexpr (MODE == 2) {                           // rows outside the box are not needed: zero
-        const int iw = wrap_half(j + ko * T, N);
-        if (iw < x.ylo || iw > x.yhi) val = make_float2(0.f, 0.f);
-      }
       d[(FIRST ? ko : ko * T) * es] = val;
     });
     j += qNT; li += rNT;
     if (li >= nl) { li -= nl; ++j; }
-  }
-  if constexpr (MODE == 2) {
-    // columns outside the bounding box: zero as well (the next O * P and its row transforms read zeros there)
-    const int ncz = N - nl, lane = tid & 31;
-    for (int row = tid >> 5; row < N; row += NT / 32)
-      for (int cz = lane; cz < ncz; cz += 32) {
-        int c = l0 + nl + cz;
-        if (c < 0) c += N;
-        else if (c >= N) c -= N;
-        dst[row * es + c] = make_float2(0.f, 0.f);
-      }
   }
   __syncthreads();
 }
@@ -227,8 +223,6 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
 
   // ---- prologue: twiddles, the grid of cell maxima, max|objF|^2 ----
   for (int t = tid; t < N; t += NT) tws[t] = p.tw[t];
-  if constexpr (PLAN)
-    for (int t = tid; t < N * PITCH; t += NT) bufF[t] = make_float2(0.f, 0.f);
   for (int t = warp; t < p.cgr * p.cgc; t += 2 * NW) {           // two cells per warp in flight
     const int t1 = t + NW;
     const float m0 = cell_part(t / p.cgc, t % p.cgc);
@@ -324,19 +318,19 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
 
     if constexpr (PLAN) {
       StageExtra x;
-      x.inv_i = stack + (size_t)slot * NN; x.ylo = p.ylo; x.yhi = p.yhi; x.epsr = epsr; x.epsi = epsi;
-      // ---- I: inverse transform, rows (only those of the bounding box: the others are zero and stay zero) then
-      //         columns; M fused into the last column stage ----
-      plan_stage<NT, R1, true, true, 0>(bufF, bufQ, tws, N, 1, PITCH, tid, p.ylo, NRb, x); FPM_TICK(2);
+      x.inv_i = stack + (size_t)slot * NN; x.epsr = epsr; x.epsi = epsi;
+      // ---- I: inverse transform, rows (only those of the bounding box: the others are zero) then columns; M fused
+      //         into the last column stage ----
+      plan_stage<NT, R1, true, true, 0, true>(bufF, bufQ, tws, N, 1, PITCH, tid, p.ylo, NRb, x, p.xlo, NCb); FPM_TICK(2);
       plan_stage<NT, R2, true, false, 0>(bufQ, bufF, tws, N, 1, PITCH, tid, p.ylo, NRb, x); FPM_TICK(3);
-      plan_stage<NT, R1, true, true, 0>(bufF, bufQ, tws, N, PITCH, 1, tid, 0, N, x); FPM_TICK(4);
+      plan_stage<NT, R1, true, true, 0, true>(bufF, bufQ, tws, N, PITCH, 1, tid, 0, N, x, p.ylo, NRb); FPM_TICK(4);
       plan_stage<NT, R2, true, false, 1>(bufQ, bufF, tws, N, PITCH, 1, tid, 0, N, x); FPM_TICK(5);
-      // ---- F: forward transform, rows then the columns of the bounding box; C fused into the last column stage
-      //         (Q replaces Phi' in bufF, zero outside the box) ----
+      // ---- F: forward transform, rows then the columns of the bounding box (outside the box bufF is stale from here
+      //         on and not read until the next M rewrites it) ----
       plan_stage<NT, R1, false, true, 0>(bufF, bufQ, tws, N, 1, PITCH, tid, 0, N, x); FPM_TICK(6);
       plan_stage<NT, R2, false, false, 0>(bufQ, bufF, tws, N, 1, PITCH, tid, 0, N, x); FPM_TICK(7);
       plan_stage<NT, R1, false, true, 0>(bufF, bufQ, tws, N, PITCH, 1, tid, p.xlo, NCb, x); FPM_TICK(8);
-      plan_stage<NT, R2, false, false, 2>(bufQ, bufF, tws, N, PITCH, 1, tid, p.xlo, NCb, x); FPM_TICK(9);
+      plan_stage<NT, R2, false, false, 0>(bufQ, bufF, tws, N, PITCH, 1, tid, p.xlo, NCb, x); FPM_TICK(9);
       // ---- C: object update (old pupil) written to the spectrum, Q from the old window in place of Phi' ----
       {
         constexpr int UC = 4;
