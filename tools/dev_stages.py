@@ -21,8 +21,17 @@ for name in names:
         v = np.array(list(buf), dtype=np.float64) / n_upd
         labels = ["-", "S1 colA(inv)+O*P", "S2 colB(inv)", "S3 rowA(inv)", "S4 rowB+amp+rowB'", "S5 rowA'", "S6 colB'", "S7 colA'", "C2 object update", "D max|objF|", "E pupil+next window"]
         if "general path, fused" in ctx.variant:
-            labels = ["-", "A P+=Q, O*P, max|P|", "I row stage 1", "I row stage 2", "I col stage 1", "I col stage 2 + M", "F row stage 1",
-                      "F row stage 2", "F col stage 1", "F col stage 2 + C", "D max|objF|"]
+            # ticks of fpm_update_general_kernel: 11 = A's element loop, 1 = its barrier + max|P|; 14 = C; 12 = D's cell
+            # rebuild, 13 = its barrier, 10 = the grid scan
+            labels = ["-", "A barrier, max|P|", "I row stage 1", "I row stage 2", "I col stage 1", "I col stage 2 + M", "F row stage 1",
+                      "F row stage 2", "F col stage 1", "F col stage 2", "D grid scan"]
+            print(name, "tiles", n_tiles, ctx.variant)
+            for k, lab in ((11, "A P+=Q, O*P (box)"), (1, labels[1])) + tuple((k, labels[k]) for k in range(2, 10)) + \
+                    ((14, "C object/pupil incr."), (12, "D cell rebuild"), (13, "D barrier"), (10, labels[10])):
+                print("   %-22s %8.0f cyc  %5.1f%%" % (lab, v[k], 100 * v[k] / v[1:16].sum()))
+            print("   total %.0f cycles/update" % v[1:16].sum())
+            ctx.close()
+            continue
         print(name, "tiles", n_tiles, ctx.variant)
         for k in range(1, 11):
             print("   %-20s %8.0f cyc  %5.1f%%" % (labels[k], v[k], 100 * v[k] / v[1:16].sum()))
