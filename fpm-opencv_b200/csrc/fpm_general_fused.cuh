@@ -251,10 +251,12 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
       const float inv_omax = pending ? rsqrt_fast(omax2) : 0.f;
       float pm2 = 0.f;
       if constexpr (PLAN) {
-        constexpr int UA = 8;
+        // batches of 8 elements per thread in flight (their global loads are issued together) while more than 4 per
+        // thread remain, then batches of 4: 61 x 61 box = one batch of 8, 75 x 75 = 8 + 4
         const int qb = NT / NCb, rb = NT % NCb;
         int bi = tid / NCb, bj = tid % NCb;
-        for (int t = tid; t < nbox; t += UA * NT) {             // UA elements in flight: their global loads are issued together
+        auto batch = [&](auto ua_tag, int t) {
+          constexpr int UA = decltype(ua_tag)::value;
           float2 pv[UA], ov[UA];
           int fo[UA], pe[UA];
 #pragma unroll
@@ -281,7 +283,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
               pm2 = fmaxf(pm2, fmaf(pv[k].x, pv[k].x, pv[k].y * pv[k].y));
               bufF[fo[k]] = cmul(ov[k], pv[k]);
             }
-        }
+        };
+        int t = tid;
+        for (; nbox - (t - tid) > 4 * NT; t += 8 * NT) batch(std::integral_constant<int, 8>{}, t);
+        for (; t < nbox; t += 4 * NT) batch(std::integral_constant<int, 4>{}, t);
       } else {
       int i = ti0, j = tj0;
       constexpr int UA = PLAN ? 8 : UN;
@@ -333,10 +338,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
       plan_stage<NT, R2, false, false, 0>(bufQ, bufF, tws, N, PITCH, 1, tid, p.xlo, NCb, x); FPM_TICK(9);
       // ---- C: object update (old pupil) written to the spectrum, Q from the old window in place of Phi' ----
       {
-        constexpr int UC = 4;
         const int qb = NT / NCb, rb = NT % NCb;
         int bi = tid / NCb, bj = tid % NCb;
-        for (int t = tid; t < nbox; t += UC * NT) {
+        auto batch = [&](auto uc_tag, int t) {
+          constexpr int UC = decltype(uc_tag)::value;
           float2 Ovs[UC], Pvs[UC];
           float sup[UC];
           int fo[UC], oo[UC];
@@ -369,7 +374,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_general_kernel(const __grid_
               const float sq = __fdividef(sqrt_fast(oa2) * sup[k], fmaf(A1, A1, kd1 * kd1));
               bufF[fo[k]] = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
             }
-        }
+        };
+        int t = tid;
+        for (; nbox - (t - tid) > 4 * NT; t += 8 * NT) batch(std::integral_constant<int, 8>{}, t);
+        for (; t < nbox; t += 4 * NT) batch(std::integral_constant<int, 4>{}, t);
       }
       FPM_TICK(14);
     } else {
