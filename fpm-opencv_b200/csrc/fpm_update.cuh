@@ -52,7 +52,6 @@ struct UpdateParams {
   const short2* crop;       // [n_leds] (x = cropXStart, y = cropYStart)
   const float2* tw;         // [N] exp(-2*pi*i*n/N)
   float2* field_gmem;       // [n_tiles][N][N+1] scratch when the field does not fit shared memory
-  float2* qbuf;             // (unused)
   int L, n_leds;
   int tile0;                // first tile of this launch
   int slot_begin, n_updates;

@@ -51,7 +51,6 @@ struct fpmb200_ctx {
   float2* twN = nullptr;       // [N]
   float2* twL = nullptr;       // [L]
   float2* field_gmem = nullptr;
-  float2* qbuf = nullptr;      // (unused: the pupil increment lives in the field buffer when it has no buffer of its own)
   float2* scratch = nullptr;   // staging: max(L*L, init batch * N*N)
   size_t scratch_elems = 0;
   int ylo = 0, yhi = -1, xlo = 0, xhi = -1;
@@ -117,7 +116,10 @@ extern "C" int fpmb200_create(int device, fpmb200_ctx** out) {
   c->device = device;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   c->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); e2 != cudaSuccess) {
+    delete c;
+    return fail(FPMB200_ERR_CUDA, "cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(e2));
+  }
   *out = c;
   return FPMB200_OK;
 }
@@ -136,13 +138,13 @@ static void drop_graphs(fpmb200_ctx* c);
 static void free_tiles(fpmb200_ctx* c) {
   drop_graphs(c);
   cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->raw); cudaFree(c->support);
-  cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch); cudaFree(c->qbuf);
+  cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch);
   cudaFree(c->gfield); cudaFree(c->gq); cudaFree(c->gcells); cudaFree(c->gscal);
   cudaFree(c->origins); cudaFree(c->frame_dev); cudaFree(c->bg_dev); cudaFree(c->mosaic_dev);
   c->origins = nullptr; c->frame_dev = nullptr; c->bg_dev = nullptr; c->mosaic_dev = nullptr;
   c->have_origins = false; c->frame_elems = c->mosaic_elems = 0;
   c->gfield = c->gq = nullptr; c->gcells = c->gscal = nullptr; c->general = false;
-  c->objFc = c->objCrop = c->pupil = c->twN = c->twL = c->field_gmem = c->scratch = c->qbuf = nullptr;
+  c->objFc = c->objCrop = c->pupil = c->twN = c->twL = c->field_gmem = c->scratch = nullptr;
   c->stack = nullptr; c->raw = nullptr; c->support = nullptr; c->crop = nullptr;
   c->have_leds = c->have_support = c->have_stack = false;
   c->n_tiles = 0;
@@ -170,20 +172,7 @@ static int upload_twiddles(fpmb200_ctx* c, float2* dst, int n) {
   return FPMB200_OK;
 }
 
-extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlarge, int n_leds) {
-  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
-  if (n_tiles <= 0 || n_leds <= 0) return fail(FPMB200_ERR_ARG, "n_tiles and n_leds must be positive");
-  auto smooth235 = [](int v) { for (int f : {2, 3, 5}) while (v % f == 0) v /= f; return v == 1; };
-  if (Np < 8 || Np > 1024 || (Np & 1) || !smooth235(Np))
-    return fail(FPMB200_ERR_ARG, "Np=%d unsupported: even, 8..1024, prime factors 2,3,5 only (fused kernels: 64, 128, 256)", Np);
-  if (Nlarge < Np || Nlarge > 3584 || (Nlarge & 1) || !smooth235(Nlarge))
-    return fail(FPMB200_ERR_ARG, "Nlarge=%d must be even, in [Np, 3584], with prime factors 2,3,5 only", Nlarge);
-  // the fused kernels need power-of-two tiles and 64-aligned spectra; everything else takes the general path
-  const bool general = !((Np == 64 || Np == 128 || Np == 256) && Nlarge % 64 == 0);
-  CK(cudaSetDevice(c->device));
-  free_tiles(c);
-  c->n_tiles = n_tiles; c->N = Np; c->L = Nlarge; c->n_leds = n_leds;
-  c->general = general;
+static int tiles_alloc_impl(fpmb200_ctx* c, int n_tiles, int Np, int Nlarge, int n_leds) {
   const size_t LL = (size_t)Nlarge * Nlarge, NN = (size_t)Np * Np;
   CK(cudaMalloc(&c->objFc, sizeof(float2) * LL * n_tiles));
   CK(cudaMalloc(&c->objCrop, sizeof(float2) * LL * n_tiles));
@@ -204,6 +193,35 @@ extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlar
   int rc;
   if ((rc = upload_twiddles(c, c->twN, Np)) != FPMB200_OK) return rc;
   if ((rc = upload_twiddles(c, c->twL, Nlarge)) != FPMB200_OK) return rc;
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlarge, int n_leds) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  if (n_tiles <= 0 || n_leds <= 0) return fail(FPMB200_ERR_ARG, "n_tiles and n_leds must be positive");
+  // tiles index gridDim.y of the batched helper kernels (initialisation, line FFTs, general path)
+  if (n_tiles > 65535) return fail(FPMB200_ERR_ARG, "n_tiles=%d exceeds 65535 tiles per context (use several contexts)", n_tiles);
+  auto smooth235 = [](int v) { for (int f : {2, 3, 5}) while (v % f == 0) v /= f; return v == 1; };
+  if (Np < 8 || Np > 1024 || (Np & 1) || !smooth235(Np))
+    return fail(FPMB200_ERR_ARG, "Np=%d unsupported: even, 8..1024, prime factors 2,3,5 only (fused kernels: 64, 128, 256)", Np);
+  if (Nlarge < Np || Nlarge > 3584 || (Nlarge & 1) || !smooth235(Nlarge))
+    return fail(FPMB200_ERR_ARG, "Nlarge=%d must be even, in [Np, 3584], with prime factors 2,3,5 only", Nlarge);
+  // the fused kernels need power-of-two tiles and 64-aligned spectra; everything else takes the general path
+  const bool general = !((Np == 64 || Np == 128 || Np == 256) && Nlarge % 64 == 0);
+  CK(cudaSetDevice(c->device));
+  free_tiles(c);
+  c->N = Np; c->L = Nlarge; c->n_leds = n_leds;
+  c->general = general;
+  // n_tiles is published only when every buffer exists: a failed allocation leaves an unallocated context
+  const int rc = tiles_alloc_impl(c, n_tiles, Np, Nlarge, n_leds);
+  if (rc != FPMB200_OK) {
+    const std::string msg = g_err;
+    cudaGetLastError();
+    free_tiles(c);
+    g_err = msg;
+    return rc;
+  }
+  c->n_tiles = n_tiles;
   snprintf(c->variant, sizeof c->variant, "allocated (support not uploaded yet)");
   return FPMB200_OK;
 }
@@ -311,6 +329,7 @@ static bool cluster_fits(fpmb200_ctx* c, int* cpc_out, int* cs_out, size_t* byte
 
 // ---- choose the kernel variant for this (N, L, bbox): CTAs per tile and what lives in shared memory ----
 static int select_variant(fpmb200_ctx* c) {
+  drop_graphs(c);              // captured passes bake in the bounding box of the support and the kernel variant
   const int N = c->N;
   const int ylo = c->ylo, yhi = c->yhi, xlo = c->xlo, xhi = c->xhi;
   CK(cudaSetDevice(c->device));
@@ -701,7 +720,7 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
   UpdateParams p;
   memset(&p, 0, sizeof p);
   p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop;
-  p.tw = c->twN; p.field_gmem = c->field_gmem; p.qbuf = c->qbuf; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first;
+  p.tw = c->twN; p.field_gmem = c->field_gmem; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first;
   p.slot_begin = slot_begin; p.n_updates = n_updates;
   p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
   p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi; p.cs = c->cs; p.ocp = c->ocp;

@@ -25,6 +25,15 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 struct Dev {
   fpmb200_ctx* c = nullptr;
   int first = 0, n = 0;       // tile range [first, first+n) of the grid
+  Dev() = default;
+  Dev(const Dev&) = delete;
+  Dev& operator=(const Dev&) = delete;
+  ~Dev() { fpmb200_destroy(c); }            // every exit path (ck() throws) releases the device state
+};
+struct DevBuf {                              // device allocation owned by a context
+  fpmb200_ctx* c = nullptr;
+  void* p = nullptr;
+  ~DevBuf() { if (p) fpmb200_device_free(c, p); }
 };
 }  // namespace
 
@@ -50,7 +59,15 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
     if (fileName.compare(fileName.length() - el, el, d->fileExtension) != 0 || fileName.find(d->filePrefix) != 0) continue;
     const int led_num = atoi(fileName.substr(pl, fileName.length() - el - pl).c_str());
     FPMimg im;
-    if (!computeLedGeometry(*d, led_num, &im)) {
+    bool pass;
+    try {
+      pass = computeLedGeometry(*d, led_num, &im);
+    } catch (const std::exception& e) {                                                      // like loadFPMDataset
+      std::cout << "ERROR: " << e.what() << std::endl;
+      closedir(dir);
+      return -1;
+    }
+    if (!pass) {
       std::cout << "Skipped LED# " << led_num << std::endl;                                  // :236
       continue;
     }
@@ -87,11 +104,16 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
   int nx = 0, ny = 0;
   tileGrid(W, H, Np, overlap, &nx, &ny);
   const int step = Np - overlap, n_tiles = nx * ny;
+  // never more devices than tiles: every context below owns at least one tile (devs[0] is the gather root)
+  const int G = (int)devices.size() < n_tiles ? (int)devices.size() : n_tiles;
   std::cout << "Full FOV: " << W << "x" << H << " frame -> " << nx << "x" << ny << " tiles of " << Np << " (overlap " << overlap
-            << "), " << n << " LEDs, " << devices.size() << " GPU(s)" << std::endl;
+            << "), " << n << " LEDs, " << G << " GPU(s)" << std::endl;
+  {
+    const int mx = W - ((nx - 1) * step + Np), my = H - ((ny - 1) * step + Np);
+    if (mx || my) std::cout << "Full FOV: " << mx << " columns on the right and " << my << " rows at the bottom are not covered by the tile grid" << std::endl;
+  }
   makePupilSupport(Np, d->naRadius, &d->pupilSupport);
-  std::vector<Dev> devs(devices.size());
-  const int G = (int)devs.size();
+  std::vector<Dev> devs(G);
   for (int g = 0; g < G; ++g) {
     Dev& v = devs[g];
     v.first = (int)((long long)n_tiles * g / G);
@@ -156,8 +178,10 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
   const int Wm = ((nx - 1) * step + Np) * f, Hm = ((ny - 1) * step + Np) * f;
   std::vector<float> mosaic((size_t)Wm * Hm);
   Dev& root = devs[0];
-  void* gathered = nullptr;
+  DevBuf gbuf;
+  void*& gathered = gbuf.p;
   if (G > 1) {
+    gbuf.c = root.c;
     ck(fpmb200_device_alloc(root.c, (unsigned long long)n_tiles * L * L * 8ull, &gathered), "fpmb200_device_alloc");
     for (Dev& v : devs)
       if (v.c)
@@ -167,13 +191,11 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
   }
   ck(fpmb200_mosaic(root.c, gathered, nx, ny, step, mosaic.data(), 0, nullptr), "fpmb200_mosaic");
   ck(fpmb200_sync(root.c), "fpmb200_sync");
-  if (gathered) fpmb200_device_free(root.c, gathered);
   d->secondsTotal = now() - t0;
   std::cout << "FP Processing Completed (Time: " << (float)d->secondsTotal << " sec)" << std::endl;                  // :489
   if (!outDir.empty()) {
     if (!fpmio::writeTiffF32(outDir + "/mosaic_amp.tif", mosaic.data(), Wm, Hm, &err)) std::cout << "ERROR: " << err << std::endl;
     else std::cout << "Wrote mosaic_amp.tif (" << Wm << "x" << Hm << ") to " << outDir << std::endl;
   }
-  for (Dev& v : devs) fpmb200_destroy(v.c);
   return 1;
 }

@@ -11,6 +11,10 @@ struct Rd {
   const std::vector<uint8_t>& b;
   bool be;
   bool ok = true;
+  uint8_t u8(size_t o) {
+    if (o + 1 > b.size()) { ok = false; return 0; }
+    return b[o];
+  }
   uint16_t u16(size_t o) {
     if (o + 2 > b.size()) { ok = false; return 0; }
     return be ? (uint16_t)((b[o] << 8) | b[o + 1]) : (uint16_t)(b[o] | (b[o + 1] << 8));
@@ -44,9 +48,11 @@ bool readTiff(const std::string& path, Image16& out, std::string* err) {
     uint32_t cnt = r.u32(e + 4);
     size_t sz = type == 3 ? 2 : type == 4 ? 4 : type == 1 ? 1 : 0;
     if (!sz) { r.ok = false; return; }
+    // a value array can never be longer than the file it lives in (guards the allocation below)
+    if ((uint64_t)sz * cnt > buf.size()) { r.ok = false; return; }
     size_t base = (sz * cnt <= 4) ? e + 8 : r.u32(e + 8);
     v.resize(cnt);
-    for (uint32_t k = 0; k < cnt; ++k) v[k] = sz == 2 ? r.u16(base + 2 * k) : sz == 4 ? r.u32(base + 4 * k) : buf[base + k];
+    for (uint32_t k = 0; k < cnt && r.ok; ++k) v[k] = sz == 2 ? r.u16(base + 2 * k) : sz == 4 ? r.u32(base + 4 * k) : r.u8(base + k);
   };
   for (int k = 0; k < n && r.ok; ++k) {
     size_t e = ifd + 2 + 12 * (size_t)k;
@@ -73,7 +79,12 @@ bool readTiff(const std::string& path, Image16& out, std::string* err) {
   if (fmt != 1) return fail(err, path + ": only unsigned-integer samples supported");
   if (spp < 1 || spp > 4 || (spp > 1 && planar != 1)) return fail(err, path + ": unsupported sample layout");
   if (rps > height) rps = height;
+  if (rps == 0) return fail(err, path + ": RowsPerStrip is 0");
   const size_t bps = bits / 8, rowb = (size_t)width * spp * bps;
+  // uncompressed: the pixels are in the file, so a directory that promises more samples than the file has bytes is
+  // malformed (and must not drive a multi-gigabyte allocation)
+  if ((uint64_t)width * height * spp * bps > buf.size()) return fail(err, path + ": image larger than the file");
+  if (!counts.empty() && counts.size() != offs.size()) return fail(err, path + ": StripByteCounts does not match StripOffsets");
   out.width = (int)width; out.height = (int)height; out.channels = (int)spp; out.bits = (int)bits;
   out.pix.assign((size_t)width * height * spp, 0);
   size_t row = 0;
@@ -81,6 +92,7 @@ bool readTiff(const std::string& path, Image16& out, std::string* err) {
     size_t rows = (height - row) < rps ? (height - row) : rps;
     size_t need = rows * rowb;
     if ((size_t)offs[s] + need > buf.size()) return fail(err, path + ": strip exceeds file");
+    if (!counts.empty() && counts[s] < need) return fail(err, path + ": StripByteCounts smaller than the strip");
     const uint8_t* src = buf.data() + offs[s];
     uint16_t* dst = out.pix.data() + row * width * spp;
     const size_t cnt = rows * width * spp;

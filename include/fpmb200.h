@@ -11,8 +11,9 @@
  * (the reference is single-threaded, fpmMain.cpp:29-33); one context per CUDA device.
  *
  * Conventions
- *   Np      low-res tile edge (`FPM_Dataset::Np`, fpmMain.h:66), 64 | 128 | 256
- *   Nlarge  high-res edge (`Nlarge == Mlarge`, fpmMain.h:70-71, fpmMain.cpp:564-565), multiple of 64
+ *   Np      low-res tile edge (`FPM_Dataset::Np`, fpmMain.h:66): any even size in 8..1024 whose prime factors are
+ *           2, 3, 5 (the shipped JSONs use 90, 100, 200; BASELINE.json's configs 64, 128, 256)
+ *   Nlarge  high-res edge (`Nlarge == Mlarge`, fpmMain.h:70-71, fpmMain.cpp:564-565): even, Np..3584, factors 2, 3, 5
  *   objF    [Nlarge][Nlarge][2] float, DC-at-corner like `FPM_Dataset::objF` (fpmMain.h:92)
  *   objCrop [Nlarge][Nlarge][2] float = IDFT_scaled(objF) (`FPM_Dataset::objCrop`, fpmMain.cpp:481)
  *   pupil   [Np][Np][2] float, DC-at-corner like `FPM_Dataset::pupil` (fpmMain.h:94)

@@ -112,18 +112,25 @@ def test_device_from_env(monkeypatch):
 
 # ---- image loader ---------------------------------------------------------------------------
 def write_tiff16(path, img, big_endian=False):
-    """uncompressed single-strip 16-bit TIFF (what the reference's datasets are)."""
-    h, w = img.shape
+    """uncompressed single-strip 16-bit TIFF (what the reference's datasets are); [h][w] grey or [h][w][3] chunky RGB."""
+    h, w = img.shape[:2]
+    spp = 1 if img.ndim == 2 else img.shape[2]
     e = ">" if big_endian else "<"
     data = img.astype(e + "u2").tobytes()
-    tags = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, 1, 16), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, 8),
-            (277, 3, 1, 1), (278, 4, 1, h), (279, 4, 1, len(data))]
+    ifd_off = 8 + len(data)
+    n_tags = 9
+    extra_off = ifd_off + 2 + 12 * n_tags + 4            # out-of-line BitsPerSample for RGB (3 shorts do not fit the entry)
+    tags = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, spp, 16 if spp == 1 else extra_off), (259, 3, 1, 1),
+            (262, 3, 1, 1 if spp == 1 else 2), (273, 4, 1, 8), (277, 3, 1, spp), (278, 4, 1, h), (279, 4, 1, len(data))]
     ifd = struct.pack(e + "H", len(tags))
     for tag, typ, cnt, val in tags:
-        ifd += struct.pack(e + "HHI", tag, typ, cnt) + (struct.pack(e + "HH", val, 0) if typ == 3 else struct.pack(e + "I", val))
+        inline_short = typ == 3 and cnt == 1
+        ifd += struct.pack(e + "HHI", tag, typ, cnt) + (struct.pack(e + "HH", val, 0) if inline_short else struct.pack(e + "I", val))
     ifd += struct.pack(e + "I", 0)
+    if spp > 1:
+        ifd += struct.pack(e + "%dH" % spp, *([16] * spp))
     with open(path, "wb") as f:
-        f.write((b"MM" if big_endian else b"II") + struct.pack(e + "HI", 42, 8 + len(data)) + data + ifd)
+        f.write((b"MM" if big_endian else b"II") + struct.pack(e + "HI", 42, ifd_off) + data + ifd)
 
 
 def test_loader_preprocessing_matches_opencv(tmp_path):
@@ -191,6 +198,43 @@ def test_tiff_reader_reads_opencv_written_files(tmp_path):
     # compressed TIFFs are rejected loudly, not mis-read
     cv2.imwrite(str(root / "iLED_0001.tif"), img, [cv2.IMWRITE_TIFF_COMPRESSION, 5])
     assert fpmhost.Dataset(str(tmp_path / "d.json")).load_images() == -1
+
+
+def test_colour_frames_keep_the_channel_the_reference_keeps(tmp_path):
+    """isColor (fpmMain.cpp:109-116, dataset_cellScope.json): imread(ANYDEPTH | COLOR) gives BGR and the reference keeps
+    channels[2] -- the red plane = sample 0 of a chunky RGB TIFF.  Checked against cv2.imread on files written by this
+    test's own writer (little and big endian) and by cv2.imwrite; a grey TIFF under isColor reads as itself (OpenCV
+    replicates it into the three channels)."""
+    cv2 = pytest.importorskip("cv2")
+    import json
+    rng = np.random.default_rng(9)
+    root = tmp_path / "frames"
+    root.mkdir()
+    pts = [(0.0, 0.0, 60.0), (4.0, 0.0, 60.0), (0.0, -4.0, 60.0), (6.0, 6.0, 60.0)]
+    cfg = {"datasetRoot": str(root) + "/", "cropSizeX": 32, "cropX": 11, "cropY": 6, "bk1cropX": 0, "bk1cropY": 50,
+           "bk2cropX": 60, "bk2cropY": 1, "bgThresh": 500, "isColor": True, "objectiveNA": 0.05, "darkfieldExpMultiplier": 2,
+           "maxIlluminationNA": 0.6, "ledCount": 8, "holeCoordinates": [[{"x": x}, {"y": y}, {"z": z}] for x, y, z in pts]}
+    (tmp_path / "d.json").write_text(json.dumps(cfg))
+    rgb = {n: rng.integers(0, 3000, (90, 100, 3)).astype(np.uint16) for n in (1, 2, 3)}
+    write_tiff16(str(root / "iLED_0001.tif"), rgb[1])
+    write_tiff16(str(root / "iLED_0002.tif"), rgb[2], big_endian=True)
+    cv2.imwrite(str(root / "iLED_0003.tif"), rgb[3][..., ::-1].copy(), [cv2.IMWRITE_TIFF_COMPRESSION, 1])    # imwrite takes BGR
+    grey = rng.integers(0, 3000, (90, 100)).astype(np.uint16)
+    write_tiff16(str(root / "iLED_0004.tif"), grey)
+    ds = fpmhost.Dataset(str(tmp_path / "d.json"))
+    assert ds.load_images() == 1 and ds.scalars.ledUsedCount == 4
+    for n in (1, 2, 3, 4):
+        bgr = cv2.imread(str(root / ("iLED_%04d.tif" % n)), cv2.IMREAD_ANYDEPTH | cv2.IMREAD_COLOR)
+        assert bgr.dtype == np.uint16 and bgr.shape == (90, 100, 3)
+        full = cv2.split(bgr)[2]                                            # fpmMain.cpp:112-115
+        assert np.array_equal(full, rgb[n][..., 0] if n < 4 else grey)
+        L = ds.led(n)
+        want, bg = fpmhost.preprocess_frame(full, 32, (11, 6), (0, 50), (60, 1), 2 if L.illumination_na > ds.scalars.objectiveNA else 1, 500)
+        assert L.bg_val == bg and np.array_equal(ds.image(n), want), n
+    # several channels without isColor: refused (the reference would reinterpret interleaved samples as grey pixels)
+    cfg["isColor"] = False
+    (tmp_path / "e.json").write_text(json.dumps(cfg))
+    assert fpmhost.Dataset(str(tmp_path / "e.json")).load_images() == -1
 
 
 # ---- ABI surface ------------------------------------------------------------------------------

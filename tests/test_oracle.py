@@ -103,3 +103,72 @@ def test_synthetic_stack_properties():
     assert c.stack.dtype == np.uint16 and c.stack.shape == (117, 64, 64) and c.stack.max() == 60000
     c2 = T.Case("cfg1_mono_np64", 1234)
     assert np.array_equal(c.stack, c2.stack)      # seeded, reproducible
+
+
+# ---- the plain-C restatement (oracle/fpm_oracle.c), used by the full-size GPU parity tests ---------------------
+@pytest.mark.parametrize("n", [2, 4, 6, 8, 10, 12, 30, 50, 64, 90, 100, 108, 128, 200, 256, 384, 600])
+def test_c_oracle_fft_matches_numpy(n):
+    import c_oracle
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    assert orc.rel_l2(c_oracle.fft1d(x, -1), np.fft.fft(x)) < 1e-14
+    assert orc.rel_l2(c_oracle.fft1d(x, +1), np.fft.ifft(x) * n) < 1e-14
+
+
+@pytest.mark.parametrize("name,n_leds,iters", [("cfg1_mono_np64", 30, 2), ("cfg7_mono_np90", 20, 2), ("cfg2_fLEDc_np128", 20, 1),
+                                               ("cfg4s_dogStomach_np200", 12, 1), ("cfg5b_cellscope2_np256", 6, 1)])
+@pytest.mark.parametrize("kappa", [1, 0])
+def test_c_oracle_matches_numpy_oracle(name, n_leds, iters, kappa):
+    """fpm_oracle.c == fpm_oracle.py to 1e-13 (power-of-two and mixed-radix tiles, both scalar readings), including a
+    start in the middle of the LED list (slot_begin) as the per-step tests use it."""
+    import c_oracle
+    c = T.Case(name, 5, n_leds)
+    a = c.oracle_run(iters, kappa)
+    b = c_oracle.run(c.stack, c.cx, c.cy, c.L, c.r, c.cfg.delta1, c.cfg.delta2, c.cfg.eps, iters, kappa)
+    assert orc.rel_l2(b.objFc, a.objFc) < 1e-13 and orc.rel_l2(b.P, a.P) < 1e-13
+    # two more updates from slot 3 on both
+    for k in (3, 4):
+        orc.update(a, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, kappa)
+    c_oracle.update_inplace(b, c.stack, c.cx, c.cy, 2, c.cfg.delta1, c.cfg.delta2, c.cfg.eps, kappa, slot_begin=3)
+    assert orc.rel_l2(b.objFc, a.objFc) < 1e-13 and orc.rel_l2(b.P, a.P) < 1e-13
+
+
+# ---- the only reference-held pin of the un-vendored cvComplex arithmetic: the per-LED op multiset ----------------
+def test_cvcomplex_op_multiset_matches_reference_profile(monkeypatch):
+    """/root/reference/output.svg:831-880 (committed as tests/golden/profile_call_counts.json by
+    tests/golden/make_profile_counts.py) records how often runFPM called every cvComplex helper in one iteration over
+    the 157 LEDs of dataset_dogStomach.json.  The op-sequence mirror that anchors the oracle must issue exactly that
+    multiset on the same geometry: 9 complexMultiply, 4 complexAbs, 3 complexDivide, 2 complexConj, 5 fftShift,
+    1 ifft2, 1 fft2 per LED, +1 complexMultiply +3 fftShift +1 fft2 at initialisation (fpmMain.cpp:310-343)."""
+    pytest.importorskip("cv2")
+    import cv2_mirror
+    want = json.load(open(os.path.join(T.GOLD, "profile_call_counts.json")))
+    counts = {}
+
+    def counted(name):
+        fn = getattr(cv2_mirror, name)
+
+        def wrapper(*a, **k):
+            counts[name] = counts.get(name, 0) + 1
+            return fn(*a, **k)
+        return wrapper
+
+    for name in want["runFPM"]:
+        monkeypatch.setattr(cv2_mirror, name, counted(name))
+    n_dft = [0]
+    real_dft = cv2_mirror.cv2.dft
+
+    def dft(src, *a, **k):
+        n_dft[0] += src.shape[0] + src.shape[1]          # 1-D transforms of a 2-D cv::dft: rows + columns
+        return real_dft(src, *a, **k)
+    monkeypatch.setattr(cv2_mirror.cv2, "dft", dft)
+    c = T.Case("cfg4s_dogStomach_np200", 3)              # the shipped dogStomach tile: Np 200, Nlarge 600
+    assert len(c.cx) == 157 and (c.N, c.L) == (200, 600)
+    cv2_mirror.run(c.stack, c.cx, c.cy, c.L, c.r, c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1, 1)
+    assert counts == {k: v["calls"] for k, v in want["runFPM"].items()}, counts
+    # K2: 127 200 one-dimensional DFT_64f = 315 x (200 + 200) + (600 + 600)
+    assert n_dft[0] == want["other"]["cv::DFT_64f"]["calls"]
+    # and per LED (initialisation subtracted)
+    per_led = {k: (counts[k] - init) // 157 for k, init in
+               (("complexMultiply", 1), ("complexAbs", 0), ("complexDivide", 0), ("complexConj", 0), ("fftShift", 3), ("ifft2", 0), ("fft2", 1))}
+    assert per_led == {"complexMultiply": 9, "complexAbs": 4, "complexDivide": 3, "complexConj": 2, "fftShift": 5, "ifft2": 1, "fft2": 1}
