@@ -12,19 +12,27 @@ fused updates, final Nlarge x Nlarge inverse FFT.  Tiles are sharded over ranks 
 collective (weak scaling: per-GPU work fixed); the only communication is the timing reduction and,
 in the full-FOV leg, the final gather.
 
-`value`  : updates/s with the stacks resident in HBM, CUDA events on the launching stream, max over ranks.
-`e2e`    : same metric through the C ABI from pinned HOST buffers: H2D of every stack and D2H of every
-           objCrop inside the timed region (chunked, copy/compute overlapped on three streams).
-`roofline`: the fused update kernel against the measured HBM peak with SURVEY 8d's algorithmic bytes
-           (18*Np^2 per update); `roofline_fp32` adds the FP32 view the north star asks for.
+`value`   : updates/s with the stacks resident in HBM, CUDA events on the launching stream, max over ranks.
+`e2e`     : same metric through the C ABI from pinned HOST buffers: H2D of every stack and D2H of every
+            objCrop inside the timed region (chunked; uploads spread over several copy streams).
+            `e2e.copy_only` repeats the identical copy schedule WITHOUT the reconstruction, so the line says
+            what the host link alone allows (the e2e leg cannot be faster than that).
+`roofline`: the fused update kernel against the binding on-chip ceiling, FP32 (SURVEY 8d FLOP count / kernel time,
+            peak = FFMA throughput measured on this GPU by bin/fpm_peaks right before the run); `roofline_hbm`
+            (SURVEY 8d's algorithmic 18*Np^2 bytes against the measured copy bandwidth, plus the DRAM bytes ncu
+            actually saw) and `roofline_smem` are the secondary views.
+other legs: `single_tile` (configs[0], [1], [2]: latency of one tile), `stress` (configs[4]: cellscope2, 193 LEDs x 50
+            iterations), `full_fov` (configs[3]'s 2560x2160 frame: 320 tiles sharded strongly over the ranks).
 `--impl reference`: the reference's CPU path (1:1 OpenCV op-sequence mirror, oracle/cv2_mirror.py --
-           the reference binary itself cannot be built here) on all host cores.
+            the reference binary itself cannot be built here) on all host cores; loads no
+            library of this repo.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -50,6 +58,14 @@ def bytes_per_update(N):            # window read + write (fp32 compl
     return 18.0 * N * N
 
 
+def config_dict(tiles, iters, N=128, L=384, n_leds=157):
+    """`config` of the JSON line -- identical for both arms (the driver compares them key by key)."""
+    return {"workload": WORKLOAD.format(iters=iters, tiles=tiles), "tiles_per_gpu": tiles, "Np": N, "Nlarge": L,
+            "n_leds": n_leds, "iterations": iters, "kappa": 1, "parallelism": "tiles sharded, no collective",
+            "l2": "inputs larger than L2 (%.1f GB of stacks + %.1f GB of spectra per GPU)" % (
+                tiles * n_leds * N * N * 2 / 1e9, tiles * L * L * 8 / 1e9)}
+
+
 def geometry(cfg_json=None):
     """LED tables through the product's own host layer (C++ libfpmhost, not the oracle)."""
     import fpmhost
@@ -59,6 +75,21 @@ def geometry(cfg_json=None):
     cx, cy = ds.crop_tables()
     return dict(N=s.Np, L=s.Nlarge, r=s.naRadius, n_leds=n, cx=cx, cy=cy, delta1=s.delta1, delta2=s.delta2, eps=s.eps,
                 support=fpmhost.pupil_support(s.Np, s.naRadius))
+
+
+def geometry_reference_arm(name="cfg4_dogStomach_np128"):
+    """The same tables for the reference arm WITHOUT loading any library of this repo: the committed golden geometry
+    (produced by the reference's own jsoncpp + std::sort, tests/golden/make_golden.py) and the oracle's config reader."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fpm_oracle as orc
+    gold = os.path.join(ROOT, "tests", "golden")
+    g = json.load(open(os.path.join(gold, "geometry_%s.json" % name)))
+    cfg = orc.config_from_json(orc.load_json_lenient(os.path.join(gold, name + ".embedded.json")))
+    byn = {l["n"]: l for l in g["leds"]}
+    cx = np.array([byn[n]["cropX"] for n in g["order"]], np.int16)
+    cy = np.array([byn[n]["cropY"] for n in g["order"]], np.int16)
+    return dict(N=cfg.Np, L=cfg.Nlarge, r=cfg.naRadius, n_leds=len(cx), cx=cx, cy=cy, delta1=float(cfg.delta1),
+                delta2=float(cfg.delta2), eps=float(cfg.eps))
 
 
 def distinct_stacks(g, k, seed0=4000):
@@ -109,12 +140,23 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def measure_peaks(device):
+    """FP32 FMA and shared-memory load throughput of this GPU, measured now (fpm-opencv_b200/bin/fpm_peaks)."""
+    exe = os.path.join(ROOT, "fpm-opencv_b200", "bin", "fpm_peaks")
+    try:
+        out = subprocess.run([exe, str(device)], capture_output=True, text=True, timeout=60)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import fpmb200
     import sharding
+    import synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -125,6 +167,7 @@ def run_b200(args):
     numa_cpus = bind_to_gpu_cpus(local)        # before the pinned buffers are allocated (first touch = local node)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks_live = measure_peaks(local) if rank == 0 else {}
     g = geometry()
     N, L, n_leds, iters = g["N"], g["L"], g["n_leds"], args.iters
     tiles = args.tiles_per_gpu
@@ -136,13 +179,13 @@ def run_b200(args):
 
     # ---- synthetic input: 8 distinct seeded tiles replicated into a pinned host buffer ----
     per_tile = n_leds * N * N
-    host_in = torch.empty((tiles, per_tile), dtype=torch.int16).pin_memory()
+    in_buf = fpmb200.HostBuffer((tiles, per_tile), np.uint16, write_combined=bool(args.write_combined))
+    out_buf = fpmb200.HostBuffer((tiles, L * L * 2), np.float32)
+    hin, hout = in_buf.array, out_buf.array
     distinct = distinct_stacks(g, 8, 4000 + 100 * rank)
-    hin = host_in.numpy().view(np.uint16)
     for t in range(tiles):
         hin[t] = distinct[t % len(distinct)].reshape(-1)
-    host_out = torch.empty((tiles, L * L * 2), dtype=torch.float32).pin_memory()
-    ctx.upload_stack_ptr(0, tiles, host_in.data_ptr(), None)
+    ctx.upload_stack_ptr(0, tiles, in_buf.ptr, None)
     ctx.sync()
 
     # a real (non-NULL) stream: the C ABI treats stream==NULL as "the context's own stream", and
@@ -190,83 +233,120 @@ def run_b200(args):
     updates_per_step_rank = tiles * n_leds * iters
     value = world * updates_per_step_rank * args.steps / (ms_max * 1e-3)
 
-    # ---- e2e: pinned host -> device -> pinned host, chunked and overlapped on three streams ----
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    # ---- e2e: pinned host -> device -> pinned host, chunked; uploads spread over several copy streams ----
+    n_in = max(1, args.h2d_streams)
+    s_ins = [torch.cuda.Stream() for _ in range(n_in)]
+    s_out = torch.cuda.Stream()
     chunk = args.chunk
+    sub = max(1, min(args.h2d_tiles, chunk))
     n_chunks = (tiles + chunk - 1) // chunk
     in_bytes, out_bytes = per_tile * 2, L * L * 8
 
     # Streaming pipeline: chunk c of step s+1 is uploaded while step s still computes (its device buffers are free
-    # as soon as chunk c of step s has been reconstructed), results are read back chunk by chunk.
-    computed = [None] * n_chunks      # chunk c reconstructed (previous step) -> its input buffers may be overwritten
-    fetched = [None] * n_chunks       # chunk c read back (previous step)     -> its objCrop may be overwritten
+    # as soon as chunk c of step s has been reconstructed), results are read back chunk by chunk.  `compute=False`
+    # runs the identical copy schedule without the reconstruction (copy-only leg); `d2h=False` drops the read-back.
+    state = {"computed": [None] * n_chunks, "fetched": [None] * n_chunks}
 
-    def step_e2e():
+    def step_e2e(compute=True, d2h=True):
+        computed, fetched = state["computed"], state["fetched"]
         start = torch.cuda.Event()
         start.record(main)
-        s_in.wait_event(start if computed[0] is None else computed[0])
+        for si in s_ins:
+            si.wait_event(start)
         for c in range(n_chunks):
             a = c * chunk
             n = min(chunk, tiles - a)
-            if computed[c] is not None:
-                s_in.wait_event(computed[c])
-            ctx.upload_stack_ptr(a, n, host_in.data_ptr() + a * in_bytes, s_in.cuda_stream)
-            e_in = torch.cuda.Event()
-            e_in.record(s_in)
-            main.wait_event(e_in)
+            for k, b in enumerate(range(a, a + n, sub)):
+                si = s_ins[k % n_in]
+                if computed[c] is not None:
+                    si.wait_event(computed[c])
+                ctx.upload_stack_ptr(b, min(sub, a + n - b), in_buf.ptr + b * in_bytes, si.cuda_stream)
+            for si in s_ins:
+                e_in = torch.cuda.Event()
+                e_in.record(si)
+                main.wait_event(e_in)
             if fetched[c] is not None:
                 main.wait_event(fetched[c])
-            ctx.init_tiles(a, n, 1, sp)
-            ctx.run(iters, a, n, sp)
-            ctx.finalize(a, n, sp)
+            if compute:
+                ctx.init_tiles(a, n, 1, sp)
+                ctx.run(iters, a, n, sp)
+                ctx.finalize(a, n, sp)
             e_c = torch.cuda.Event()
             e_c.record(main)
             computed[c] = e_c
-            s_out.wait_event(e_c)
-            ctx.download_objcrop_ptr(a, n, host_out.data_ptr() + a * out_bytes, s_out.cuda_stream)
-            e_o = torch.cuda.Event()
-            e_o.record(s_out)
-            fetched[c] = e_o
+            if d2h:
+                s_out.wait_event(e_c)
+                ctx.download_objcrop_ptr(a, n, out_buf.ptr + a * out_bytes, s_out.cuda_stream)
+                e_o = torch.cuda.Event()
+                e_o.record(s_out)
+                fetched[c] = e_o
 
     def drain_e2e():
-        for e_o in fetched:
+        for e_o in state["fetched"]:
             if e_o is not None:
                 main.wait_event(e_o)
 
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    drain_e2e()
-    barrier()
-    computed = [None] * n_chunks
-    fetched = [None] * n_chunks
-    e2, e3 = ev(), ev()
-    e2.record(main)
-    for _ in range(args.steps):
-        step_e2e()
-    drain_e2e()                      # every result of every timed step is in host memory before the clock stops
-    e3.record(main)
-    barrier()
-    ms_e2e = sharding.max_over_ranks(e2.elapsed_time(e3), "cuda")
-    e2e_value = world * updates_per_step_rank * args.steps / (ms_e2e * 1e-3)
-    checksum = float(np.abs(host_out.numpy()[:: max(1, tiles // 8), :4096]).sum())
+    def timed_e2e(n_steps, n_warm, **kw):
+        for _ in range(n_warm):
+            step_e2e(**kw)
+        drain_e2e()
+        barrier()
+        state["computed"] = [None] * n_chunks
+        state["fetched"] = [None] * n_chunks
+        a, b = ev(), ev()
+        a.record(main)
+        for _ in range(n_steps):
+            step_e2e(**kw)
+        drain_e2e()                  # every result of every timed step is in host memory before the clock stops
+        b.record(main)
+        barrier()
+        state["computed"] = [None] * n_chunks
+        state["fetched"] = [None] * n_chunks
+        return sharding.max_over_ranks(a.elapsed_time(b), "cuda") / n_steps
 
-    # ---- full-FOV leg (strong scaling): BASELINE configs[3] frame 2560x2160 -> 20x16 = 320 tiles
-    #      sharded over the ranks, final gather of objCrop to rank 0 ----
+    ms_e2e = timed_e2e(args.steps, max(1, args.warmup // 2))
+    e2e_value = world * updates_per_step_rank / (ms_e2e * 1e-3)
+    checksum = float(np.abs(hout[:: max(1, tiles // 8), :4096]).sum())
+    # the same copies with no reconstruction in between: what the host link alone allows
+    ms_copy = timed_e2e(3, 1, compute=False)
+    ms_h2d = timed_e2e(3, 1, compute=False, d2h=False)
+    copy_only = {"ms_per_step": ms_copy, "h2d_only_ms_per_step": ms_h2d,
+                 "h2d_gbs_per_gpu": tiles * in_bytes / (ms_h2d * 1e-3) / 1e9,
+                 "h2d_gbs_aggregate": world * tiles * in_bytes / (ms_h2d * 1e-3) / 1e9,
+                 "both_directions_gbs_aggregate": world * tiles * (in_bytes + out_bytes) / (ms_copy * 1e-3) / 1e9,
+                 "updates_per_s_if_copy_bound": world * updates_per_step_rank / (ms_copy * 1e-3),
+                 "what": "identical schedule (same pinned buffers, chunks, streams, uint16->1/I conversion kernel) without init/run/finalize"}
+
+    # ---- full-FOV leg (strong scaling): BASELINE configs[3] frame 2560x2160 -> 20x16 = 320 tiles sharded over the
+    #      ranks, each rank in a context of its own size (so the library's few-tiles policy sees the real count),
+    #      5 timed passes, final gather of objCrop to rank 0 ----
     fov_tiles = len(sharding.tile_grid(2560, 2160, N))
     a, b = sharding.shard_range(fov_tiles, rank, world)
-    nl = min(b - a, tiles)
-    barrier()
-    f0, f1 = ev(), ev()
-    f0.record(main)
-    if nl:
-        ctx.init_tiles(0, nl, 1, sp)
-        ctx.run(iters, 0, nl, sp)
-        ctx.finalize(0, nl, sp)
-    f1.record(main)
-    torch.cuda.synchronize()
+    nl = b - a
+    fctx = fpmb200.Context(local)
+    fctx.tiles_alloc(max(nl, 1), N, L, n_leds)
+    fctx.set_params(g["delta1"], g["delta2"], g["eps"], 1)
+    fctx.upload_leds(g["cx"], g["cy"])
+    fctx.upload_pupil_support(g["support"])
+    for t in range(max(nl, 1)):
+        fctx.upload_stack(t, distinct[t % len(distinct)])
+    fov_pass = []
+    for rep in range(6):                          # first pass = warm-up
+        barrier()
+        f0, f1 = ev(), ev()
+        f0.record(main)
+        if nl:
+            fctx.init_tiles(0, nl, 1, sp)
+            fctx.run(iters, 0, nl, sp)
+            fctx.finalize(0, nl, sp)
+        f1.record(main)
+        torch.cuda.synchronize()
+        t_ms = sharding.max_over_ranks(f0.elapsed_time(f1), "cuda")
+        if rep:
+            fov_pass.append(t_ms)
     gather_ms = 0.0
     if world > 1:
-        dev_out = ctx.objcrop_tensor(0, nl) if nl else torch.empty((0, L * L * 2), dtype=torch.float32, device="cuda")
+        dev_out = fctx.objcrop_tensor(0, nl) if nl else torch.empty((0, L * L * 2), dtype=torch.float32, device="cuda")
         # first pass untimed (NCCL sets its point-to-point channels up lazily), second pass timed on the device
         for timed in (False, True):
             barrier()
@@ -278,40 +358,79 @@ def run_b200(args):
             del full
             if timed:
                 gather_ms = g0.elapsed_time(g1)
-    fov_ms = sharding.max_over_ranks(f0.elapsed_time(f1), "cuda")
+    fov_ms = float(np.median(fov_pass))
     gather_s = sharding.max_over_ranks(gather_ms, "cuda") * 1e-3
+    fov_variant = fctx.variant
+    fctx.close()
 
-    # ---- single-tile leg: BASELINE configs[1] (dataset_fLED-c.json optics, one 128x128 tile, 89 LEDs, pupil recovery on):
-    #      a latency number -- one tile is one thread-block cluster (4 SMs), the LED order is sequential ----
+    # ---- stress leg: BASELINE configs[4] (cellscope2 dome, 128x128 tiles, Nlarge 512, 193 LEDs, 50 iterations),
+    #      148 tiles per GPU (one wave), weak scaling like the headline ----
+    stress = None
+    try:
+        g5 = geometry(os.path.join(ROOT, "configs", "cfg5_cellscope2_np128.json"))
+        st_tiles, st_iters = 148, 50
+        c5 = fpmb200.Context(local)
+        c5.tiles_alloc(st_tiles, g5["N"], g5["L"], g5["n_leds"])
+        c5.set_params(g5["delta1"], g5["delta2"], g5["eps"], 1)
+        c5.upload_leds(g5["cx"], g5["cy"])
+        c5.upload_pupil_support(g5["support"])
+        s5 = [synth.synth_stack(g5["N"], g5["L"], g5["r"], g5["cx"], g5["cy"], 7000 + 10 * rank + i) for i in range(2)]
+        for t in range(st_tiles):
+            c5.upload_stack(t, s5[t % 2])
+        best = None
+        for rep in range(3):
+            barrier()
+            s0, s1 = ev(), ev()
+            s0.record(main)
+            c5.init_tiles(0, st_tiles, 1, sp)
+            c5.run(st_iters, 0, st_tiles, sp)
+            c5.finalize(0, st_tiles, sp)
+            s1.record(main)
+            torch.cuda.synchronize()
+            t_ms = sharding.max_over_ranks(s0.elapsed_time(s1), "cuda")
+            if rep:
+                best = min(best or 1e30, t_ms)
+        stress = {"workload": "cellscope2 optics (configs[4]), 128x128 tiles, Nlarge %d, %d LEDs, %d iterations, %d tiles/GPU" % (
+                      g5["L"], g5["n_leds"], st_iters, st_tiles),
+                  "ms_per_pass": best, "updates_per_s": world * st_tiles * g5["n_leds"] * st_iters / (best * 1e-3),
+                  "scaling": "weak", "kernel": c5.variant}
+        c5.close()
+    except Exception as e:
+        stress = {"error": repr(e)}
+
+    # ---- single-tile legs: BASELINE configs[0], [1], [2] -- latency numbers: the LED order is sequential, one tile can
+    #      use one SM (or one thread-block cluster) ----
     single = None
     if rank == 0:
-        try:
-            import synth
-            g1 = geometry(os.path.join(ROOT, "configs", "cfg2_fLEDc_np128.json"))
-            c1 = fpmb200.Context(local)
-            c1.tiles_alloc(1, g1["N"], g1["L"], g1["n_leds"])
-            c1.set_params(g1["delta1"], g1["delta2"], g1["eps"], 1)
-            c1.upload_leds(g1["cx"], g1["cy"])
-            c1.upload_pupil_support(g1["support"])
-            c1.upload_stack(0, synth.synth_stack(g1["N"], g1["L"], g1["r"], g1["cx"], g1["cy"], 5000))
-            best = None
-            for rep in range(4):                      # first pass = warm-up
-                c1.init_tiles(0, 1, 1, sp)
-                s0, s1 = ev(), ev()
-                s0.record(main)
-                c1.run(iters, 0, 1, sp)
-                c1.finalize(0, 1, sp)
-                s1.record(main)
-                torch.cuda.synchronize()
-                if rep:
-                    best = min(best or 1e30, s0.elapsed_time(s1))
-            single = {"workload": "fLED-c optics (configs[1]), one 128x128 tile, Nlarge %d, %d LEDs, %d iterations" % (
-                          g1["L"], g1["n_leds"], iters),
-                      "recon_ms": best, "us_per_update": best * 1e3 / (g1["n_leds"] * iters),
-                      "updates_per_s": g1["n_leds"] * iters / (best * 1e-3), "kernel": c1.variant}
-            c1.close()
-        except Exception as e:                        # the headline legs above do not depend on this one
-            single = {"error": repr(e)}
+        single = []
+        for cfg, what in (("cfg1_mono_np64", "mono optics (configs[0]), one 64x64 tile"),
+                          ("cfg2_fLEDc_np128", "fLED-c optics (configs[1]), one 128x128 tile"),
+                          ("cfg3_cellScope_np256", "cellScope dome (configs[2]), one 256x256 tile")):
+            try:
+                g1 = geometry(os.path.join(ROOT, "configs", cfg + ".json"))
+                c1 = fpmb200.Context(local)
+                c1.tiles_alloc(1, g1["N"], g1["L"], g1["n_leds"])
+                c1.set_params(g1["delta1"], g1["delta2"], g1["eps"], 1)
+                c1.upload_leds(g1["cx"], g1["cy"])
+                c1.upload_pupil_support(g1["support"])
+                c1.upload_stack(0, synth.synth_stack(g1["N"], g1["L"], g1["r"], g1["cx"], g1["cy"], 5000))
+                best = None
+                for rep in range(4):                      # first pass = warm-up
+                    c1.init_tiles(0, 1, 1, sp)
+                    s0, s1 = ev(), ev()
+                    s0.record(main)
+                    c1.run(iters, 0, 1, sp)
+                    c1.finalize(0, 1, sp)
+                    s1.record(main)
+                    torch.cuda.synchronize()
+                    if rep:
+                        best = min(best or 1e30, s0.elapsed_time(s1))
+                single.append({"workload": "%s, Nlarge %d, %d LEDs, %d iterations" % (what, g1["L"], g1["n_leds"], iters),
+                               "recon_ms": best, "us_per_update": best * 1e3 / (g1["n_leds"] * iters),
+                               "updates_per_s": g1["n_leds"] * iters / (best * 1e-3), "kernel": c1.variant})
+                c1.close()
+            except Exception as e:                        # the headline legs above do not depend on these
+                single.append({"workload": what, "error": repr(e)})
 
     if rank == 0:
         peaks = {}
@@ -321,9 +440,17 @@ def run_b200(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        if "fp32_ffma_tflops" in peaks_live:
+            fp32_peak = max(peaks_live["fp32_ffma_tflops"], peaks_live.get("fp32_ffma2_tflops", 0.0))
+            smem_peak = peaks_live["smem_lds128_tbs"]
+            onchip_src = "measured on this GPU right before the run (bin/fpm_peaks: FFMA/FFMA2 chains, conflict-free LDS.128)"
+        else:
+            fp32_peak, smem_peak = FP32_PEAK_TFLOPS_NOMINAL, SMEM_PEAK_TBS_NOMINAL
+            onchip_src = "nominal 148 SM x 128 lanes x 2 x 1.965 GHz / 148 SM x 128 B/clk (SURVEY 8d); fpm_peaks failed: %s" % peaks_live.get("error")
         upd_per_launch = tiles * n_leds * iters
         ach_gbs = bytes_per_update(N) * upd_per_launch / (kernel_ms * 1e-3) / 1e9
         ach_tf = flops_per_update(N) * upd_per_launch / (kernel_ms * 1e-3) / 1e12
+        ach_smem = 48.0 * N * N * upd_per_launch / (kernel_ms * 1e-3) / 1e12
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
         # (profiles/traffic.json); per launch like `achieved`, scaled by updates when this launch is a different size
         traffic = None
@@ -332,46 +459,47 @@ def run_b200(args):
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * (upd_per_launch / tj["updates_per_launch"])
         except Exception:
             pass
+        cfgd = config_dict(tiles, iters, N, L, n_leds)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (complex64 field, uint16 intensities)", "data": "synthetic (8 seeded tiles/rank replicated; forward model of the reference)",
-            "config": {"workload": WORKLOAD.format(iters=iters, tiles=tiles), "tiles_per_gpu": tiles, "Np": N, "Nlarge": L,
-                       "n_leds": n_leds, "iterations": iters, "kappa": 1, "parallelism": "tiles sharded, no collective",
-                       "l2": "inputs larger than L2 (%.1f GB of stacks + %.1f GB of spectra per GPU)" % (
-                           tiles * in_bytes / 1e9, tiles * out_bytes / 1e9),
-                       "kernel": ctx.variant},
+            "config": cfgd,
+            "kernel": ctx.variant,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tiles * in_bytes * world,
-                    "d2h_bytes_per_step": tiles * out_bytes * world, "ms_per_step": ms_e2e / args.steps,
-                    "chunk_tiles": chunk, "checksum": checksum,
-                    "host_cpus_bound": numa_cpus,
+                    "d2h_bytes_per_step": tiles * out_bytes * world, "ms_per_step": ms_e2e,
+                    "chunk_tiles": chunk, "h2d_streams": n_in, "h2d_copy_tiles": sub, "write_combined_input": bool(args.write_combined),
+                    "checksum": checksum, "host_cpus_bound": numa_cpus, "copy_only": copy_only,
                     "pipeline": "per step: H2D of every stack + reconstruction + D2H of every objCrop; uploads of step s+1 overlap the compute of step s"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)", "kernel": "fpm_update_kernel", "kernel_ms_per_launch": kernel_ms,
-                         "algorithmic_bytes_per_update": bytes_per_update(N), "updates_per_launch": upd_per_launch,
-                         "peak_source": peak_src},
-            "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": FP32_PEAK_TFLOPS_NOMINAL, "unit": "TFLOP/s",
-                              "frac": ach_tf / FP32_PEAK_TFLOPS_NOMINAL, "flops_per_update": flops_per_update(N),
-                              "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (SURVEY 8d)"},
-            # SURVEY 8d's shared-memory lower bound (48*Np^2 bytes per update: one transpose per 2-D FFT + stage in/out)
-            # against 148 SMs x 128 B/clk x f_max; the ncu capture under profiles/ has the actual wavefront count
-            # (12.4 k per update = 61 % of the pipe: the unit that binds this kernel)
-            "roofline_smem": {"bound": "smem", "achieved": 48.0 * N * N * upd_per_launch / (kernel_ms * 1e-3) / 1e12,
-                              "peak": SMEM_PEAK_TBS_NOMINAL, "unit": "TB/s",
-                              "frac": 48.0 * N * N * upd_per_launch / (kernel_ms * 1e-3) / 1e12 / SMEM_PEAK_TBS_NOMINAL,
-                              "bytes_per_update": 48.0 * N * N,
-                              "peak_source": "nominal 148 SM x 128 B/clk x 1.965 GHz (SURVEY 8d)"},
-            "full_fov": {"frame": "2560x2160", "tiles": fov_tiles, "recon_ms": fov_ms, "gather_s": gather_s,
-                         "updates_per_s": fov_tiles * n_leds * iters / (fov_ms * 1e-3), "scaling": "strong"},
+            "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram read+write)",
+                         "kernel": "fpm_update_kernel", "kernel_ms_per_launch": kernel_ms,
+                         "flops_per_update": flops_per_update(N), "updates_per_launch": upd_per_launch,
+                         "peak_source": onchip_src, "peak_nominal": FP32_PEAK_TFLOPS_NOMINAL},
+            "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                             "algorithmic_bytes_per_update": bytes_per_update(N), "peak_source": peak_src,
+                             "dram_gbs_actual": None if traffic is None else traffic / (kernel_ms * 1e-3) / 1e9,
+                             "note": "SURVEY 8d counts the whole window in HBM; the window lives in L2, DRAM sees the 1/I stream (dram_gbs_actual)"},
+            # SURVEY 8d's shared-memory lower bound (48*Np^2 bytes per update: one transpose per 2-D FFT + stage in/out);
+            # the ncu capture under profiles/ has the actual wavefront count
+            "roofline_smem": {"bound": "smem", "achieved": ach_smem, "peak": smem_peak, "unit": "TB/s",
+                              "frac": ach_smem / smem_peak, "bytes_per_update": 48.0 * N * N, "peak_source": onchip_src},
+            "peaks_measured": peaks_live,
+            "full_fov": {"frame": "2560x2160", "tiles": fov_tiles, "recon_ms": fov_ms, "recon_ms_passes": fov_pass, "gather_s": gather_s,
+                         "updates_per_s": fov_tiles * n_leds * iters / (fov_ms * 1e-3), "scaling": "strong", "kernel": fov_variant},
         }
+        if stress is not None:
+            line["stress"] = stress
         if single is not None:
             line["single_tile"] = single
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(g, distinct[0], iters)
         print(json.dumps(line), flush=True)
     ctx.close()
+    in_buf.close()
+    out_buf.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -409,11 +537,12 @@ def _ref_worker(a):
 
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path, all host cores, one tile per
-    worker process (tiles are independent).  Under torchrun only rank 0 works."""
+    worker process (tiles are independent).  Under torchrun only rank 0 works.  No library of this repo is loaded:
+    geometry comes from the committed golden tables, stacks from numpy."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import multiprocessing as mp
-    g = geometry()
+    g = geometry_reference_arm()
     cores = os.cpu_count() or 1
     stacks = distinct_stacks(g, min(cores, 8))
     n_updates = args.ref_updates
@@ -430,8 +559,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (CV_64FC2, uint16 intensities)", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(iters=args.iters, tiles=args.tiles_per_gpu), "Np": g["N"], "Nlarge": g["L"],
-                       "n_leds": g["n_leds"], "kappa": 1, "host_cores": cores},
+            "config": config_dict(args.tiles_per_gpu, args.iters, g["N"], g["L"], g["n_leds"]),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -443,6 +571,7 @@ def bind_to_gpu_cpus(local):
     Returns the number of CPUs in the mask (0 = left unchanged)."""
     try:
         import pynvml
+        import torch
         pynvml.nvmlInit()
         try:
             uuid = str(torch.cuda.get_device_properties(local).uuid)
@@ -468,6 +597,9 @@ def main():
     ap.add_argument("--tiles-per-gpu", type=int, default=592)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--chunk", type=int, default=148)
+    ap.add_argument("--h2d-streams", type=int, default=2, help="copy streams the uploads of one chunk are spread over")
+    ap.add_argument("--h2d-tiles", type=int, default=12, help="tiles per upload call (12 tiles = 62 MB)")
+    ap.add_argument("--write-combined", type=int, default=0, help="1: write-combined pinned input buffer")
     ap.add_argument("--ref-updates", type=int, default=157)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -958,6 +958,17 @@ extern "C" int fpmb200_copy_objcrop_to(fpmb200_ctx* src, int tile_first, int n, 
   return FPMB200_OK;
 }
 
+extern "C" int fpmb200_host_alloc(unsigned long long bytes, int write_combined, void** ptr) {
+  if (!ptr || !bytes) return fail(FPMB200_ERR_ARG, "NULL argument or zero size");
+  *ptr = nullptr;
+  CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return FPMB200_OK;
+}
+extern "C" int fpmb200_host_free(void* ptr) {
+  if (ptr) CK(cudaFreeHost(ptr));
+  return FPMB200_OK;
+}
+
 extern "C" int fpmb200_sync(fpmb200_ctx* c) {
   if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
   CK(cudaSetDevice(c->device));

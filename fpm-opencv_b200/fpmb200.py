@@ -59,6 +59,8 @@ def load():
         "fpmb200_device_alloc": (i, [vp, C.c_ulonglong, C.POINTER(vp)]),
         "fpmb200_device_free": (i, [vp, vp]),
         "fpmb200_copy_objcrop_to": (i, [vp, i, i, vp, vp, vp]),
+        "fpmb200_host_alloc": (i, [C.c_ulonglong, i, C.POINTER(vp)]),
+        "fpmb200_host_free": (i, [vp]),
         "fpmb200_sync": (i, [vp]),
         "fpmb200_kernel_launches": (C.c_longlong, [vp]),
         "fpmb200_variant": (C.c_char_p, [vp]),
@@ -76,11 +78,36 @@ EXPORTS = ["fpmb200_last_error", "fpmb200_abi_version", "fpmb200_create", "fpmb2
            "fpmb200_step", "fpmb200_finalize", "fpmb200_upload_state", "fpmb200_download",
            "fpmb200_download_objcrop", "fpmb200_device_buffer", "fpmb200_set_tile_origins", "fpmb200_ingest_frame",
            "fpmb200_ingest_bg", "fpmb200_mosaic", "fpmb200_device_alloc", "fpmb200_device_free", "fpmb200_copy_objcrop_to",
-           "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
+           "fpmb200_host_alloc", "fpmb200_host_free", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
 
 
 class FpmError(RuntimeError):
     pass
+
+
+class HostBuffer:
+    """Page-locked host memory from fpmb200_host_alloc as a numpy array (freed with the object)."""
+
+    def __init__(self, shape, dtype, write_combined=False):
+        self.L = load()
+        self.array = None
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        if self.L.fpmb200_host_alloc(n, int(write_combined), C.byref(p)) != 0:
+            raise FpmError(self.L.fpmb200_last_error().decode())
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_ubyte)), shape=(n,)).view(dtype).reshape(shape)
+
+    def close(self):
+        if self.array is not None:
+            self.array = None
+            self.L.fpmb200_host_free(C.c_void_p(self.ptr))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _ptr(a):

@@ -133,6 +133,13 @@ int fpmb200_device_alloc(fpmb200_ctx* ctx, unsigned long long bytes, void** ptr)
 int fpmb200_device_free(fpmb200_ctx* ctx, void* ptr);
 int fpmb200_copy_objcrop_to(fpmb200_ctx* src, int tile_first, int n, fpmb200_ctx* dst, void* dst_ptr, void* stream);
 
+/* Page-locked host staging memory for the asynchronous copies above (frames for fpmb200_ingest_frame, stacks for
+ * fpmb200_upload_stack, results of fpmb200_download_objcrop).  write_combined != 0 asks for write-combined pages:
+ * faster for the device to read over PCIe on some hosts, slow for the CPU to read back -- input buffers only.
+ * The reference has no counterpart (cv::UMat::getMat maps pageable memory, fpmMain.cpp:380-381). */
+int fpmb200_host_alloc(unsigned long long bytes, int write_combined, void** ptr);
+int fpmb200_host_free(void* ptr);
+
 int fpmb200_sync(fpmb200_ctx* ctx);
 
 /* Introspection: kernels launched by this context so far, and the name/shape of the update
