@@ -597,8 +597,11 @@ def main():
     ap.add_argument("--tiles-per-gpu", type=int, default=592)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--chunk", type=int, default=148)
-    ap.add_argument("--h2d-streams", type=int, default=2, help="copy streams the uploads of one chunk are spread over")
-    ap.add_argument("--h2d-tiles", type=int, default=12, help="tiles per upload call (12 tiles = 62 MB)")
+    # one upload call per chunk on one stream: measured on one B200, 13 calls of 12 tiles on two streams HALVED e2e
+    # (7.96 M vs 13.2 M updates/s): every call ends with the uint16 -> 1/I conversion kernel, which needs an SM and
+    # waits for a CTA of the persistent update kernel to retire (16.8 ms) -- the copies queued behind it stall
+    ap.add_argument("--h2d-streams", type=int, default=1, help="copy streams the uploads of one chunk are spread over")
+    ap.add_argument("--h2d-tiles", type=int, default=148, help="tiles per upload call (12 tiles = 62 MB)")
     ap.add_argument("--write-combined", type=int, default=0, help="1: write-combined pinned input buffer")
     ap.add_argument("--ref-updates", type=int, default=157)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -32,6 +32,16 @@ def _gpu():
     _need_gpu()
 
 
+def note(msg):
+    """Parity numbers worth keeping: printed, and appended to gpurun_out/parity_notes.txt when that directory exists
+    (the GPU runner brings it back; summaries are committed under profiles/)."""
+    print(msg)
+    d = os.path.join(T.ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_notes.txt"), "a") as f:
+            f.write(msg + "\n")
+
+
 def compare(ctx, st, tile=0, tol=FULL_TOL, crop=True):
     gF, gC, gP = ctx.download(tile, objCrop=crop)
     eF, eP = orc.rel_l2(gF, T.corner(st.objFc)), orc.rel_l2(gP, st.P)
@@ -88,7 +98,7 @@ def test_per_step_parity(name, n_steps, kappa, ctas):
         orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, kappa)
         ctx.step(0, k)
         worst = max(worst, *compare(ctx, st, tol=STEP_TOL, crop=False))
-    print("%s kappa=%d worst per-step rel-L2 %.2e" % (name, kappa, worst))
+    note("per-step %s kappa=%d ctas=%d: worst rel-L2 over %d updates %.2e [%s]" % (name, kappa, ctas, min(n_steps, len(c.cx)), worst, ctx.variant[:60]))
     ctx.close()
 
 
@@ -107,7 +117,7 @@ def test_full_run_parity(name, iters, ctas):
     ctx.finalize()
     st = c.oracle_run(iters)
     e = compare(ctx, st)
-    print("%s %d iterations x %d LEDs: rel-L2 objF %.2e pupil %.2e [%s]" % (name, iters, len(c.cx), e[0], e[1], ctx.variant))
+    note("full run %s %d iterations x %d LEDs: rel-L2 objF %.2e pupil %.2e [%s]" % (name, iters, len(c.cx), e[0], e[1], ctx.variant))
     ctx.close()
 
 
@@ -614,13 +624,18 @@ def test_full_size_oracle_parity(name, iters):
     st = _full_size_oracle(name, iters)
     for ctx, _ in got:
         e = compare(ctx, st)
-        print("%s %d iterations x %d LEDs = %d updates: rel-L2 objF %.2e pupil %.2e [%s]" % (
+        note("full size %s %d iterations x %d LEDs = %d updates: rel-L2 objF %.2e pupil %.2e [%s]" % (
             name, iters, len(c.cx), iters * len(c.cx), e[0], e[1], ctx.variant))
     if len(got) == 2:
         assert "cluster_kernel" in got[1][0].variant and "cluster_kernel" not in got[0][0].variant
-        # same butterflies in the same order per element, exact maxima: how a tile is spread over SMs does not change a bit
-        for x, y in zip(got[0][1], got[1][1]):
-            assert np.array_equal(x, y)
+        if "pruned radix-16" in got[0][0].variant:
+            # the one-CTA kernel's pruned first butterfly layer adds in another order than the cluster kernel's full one
+            for x, y in zip(got[0][1], got[1][1]):
+                assert orc.rel_l2(x, y) < 1e-5
+        else:
+            # same butterflies in the same order per element, exact maxima: how a tile is spread over SMs does not change a bit
+            for x, y in zip(got[0][1], got[1][1]):
+                assert np.array_equal(x, y)
     for ctx, _ in got:
         ctx.close()
 
