@@ -278,7 +278,7 @@ template <int R, bool INV> __host__ __device__ __forceinline__ void fftR(float2 
   else static_assert(R == 16, "unsupported radix");
 }
 
-// ---- composite radices 6, 9, 10 (mixed-radix tiles: Np = 90 = 9 x 10, 100 = 10 x 10 ...) --------------------------
+// ---- composite radices 6, 9, 10, 12, 15, 20, 25 (mixed-radix tiles: Np = 90 = 9 x 10, 100 = 10 x 10, 200 = 20 x 10 ...) --------------------------
 // cos / sin by Taylor series in double, for compile-time roots of unity (|x| <= pi: 17 terms reach 1e-16)
 __host__ __device__ constexpr double cx_cos(double x) {
   double s = 1.0, t = 1.0;
@@ -302,6 +302,10 @@ template <int R> struct RadixSplit { static constexpr int A = R, B = 1; };
 template <> struct RadixSplit<6> { static constexpr int A = 2, B = 3; };
 template <> struct RadixSplit<9> { static constexpr int A = 3, B = 3; };
 template <> struct RadixSplit<10> { static constexpr int A = 2, B = 5; };
+template <> struct RadixSplit<12> { static constexpr int A = 4, B = 3; };
+template <> struct RadixSplit<15> { static constexpr int A = 3, B = 5; };
+template <> struct RadixSplit<20> { static constexpr int A = 4, B = 5; };
+template <> struct RadixSplit<25> { static constexpr int A = 5, B = 5; };
 // fft_reg<R> leaves X[radix_out<R>(i)] in v[i] (slot B*k1 + k2 holds X[k1 + A*k2]); the caller folds the permutation
 // into its store addresses
 template <int R> __host__ __device__ constexpr int radix_out(int i) {

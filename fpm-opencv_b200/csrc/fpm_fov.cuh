@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(1024) ingest_bg_kernel(const uint16_t* frame, 
 
 // ROI cut + cv::divide (round half to even, x/0 -> 0) + saturating background subtraction for every tile
 // (blockIdx.y) of one LED frame; writes the uint16 result and 1/I in the update kernels' stack layout.
-// perm = 1: stack_offset<N> order of the fused kernels (R1 x R2 factorisation), 0: natural order.
+// perm = 1: stack_offset<N> order of the fused kernels (R1 x R2 factorisation), 2: position-major order of
+// fpm_pruned_fused.cuh (stack_pos_offset), 0: natural order.
 __global__ void __launch_bounds__(256) ingest_tiles_kernel(const uint16_t* frame, int w, const int2* origin, int tile0,
                                                            uint16_t* raw, float* stack, int n_leds, int slot, int Np, int R1,
                                                            int perm, int divisor, const int* bg) {
@@ -61,9 +62,11 @@ __global__ void __launch_bounds__(256) ingest_tiles_kernel(const uint16_t* frame
     v = v < 0 ? 0 : v > 65535 ? 65535 : v;
     raw[base + t] = (uint16_t)v;
     int off = t;
-    if (perm) {
+    if (perm == 1) {
       const int pos = R2 * (y % R1) + y / R1;
       off = ((x % R1) * Np + pos) * R2 + x / R1;
+    } else if (perm == 2) {
+      off = (R2 * (y % R1) + y / R1) * Np + R2 * (x % R1) + x / R1;
     }
     stack[base + off] = 1.0f / (float)v;
   }

@@ -37,9 +37,18 @@ struct GeneralParams {
   int ylo, xlo, nrb, ncb;   // bounding box of the pupil support: first wrapped row / column (in [-N/2, N/2)), extent
   float delta1, delta2, eps, kappa;
   int apply;                // gen_pupil_update: 0 = only reduce max|P|^2 (start of a launch sequence)
+  int stack_r1;             // stack layout (stack_pos_offset): 0 = natural
 };
 
 __device__ __forceinline__ int wrap_half(int i, int N) { return (i < N / 2) ? i : i - N; }
+// Stack layouts of the general path: R1 == 0 natural order [y][x]; R1 > 0 position-major [pos(y)][pos(x)] with
+// pos(v) = R2*(v % R1) + v / R1, R2 = N / R1 -- the order in which the two-stage in-place transforms of
+// fpm_pruned_fused.cuh leave the field, so that its amplitude stage reads 1/I coalesced.
+__host__ __device__ __forceinline__ int stack_pos_offset(int y, int x, int N, int R1) {
+  if (R1 == 0) return y * N + x;
+  const int R2 = N / R1;
+  return (R2 * (y % R1) + y / R1) * N + R2 * (x % R1) + x / R1;
+}
 
 __global__ void __launch_bounds__(256) gen_window_mul(const GeneralParams p) {
   const int tile = p.tile0 + blockIdx.y, N = p.N, L = p.L, H = N / 2;
@@ -63,7 +72,7 @@ __global__ void __launch_bounds__(256) gen_amplitude(const GeneralParams p) {
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N * N; t += gridDim.x * blockDim.x) {
     const float2 v = F[t];
     const float2 tt = make_float2(v.x + er, v.y + ei);
-    const float sc = rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y) * inv_i[t]);     // sqrt(I)/|psi+eps|; I = 0 -> 0
+    const float sc = rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y) * inv_i[stack_pos_offset(t / N, t % N, N, p.stack_r1)]);   // sqrt(I)/|psi+eps|; I = 0 -> 0
     F[t] = make_float2(v.x * sc, v.y * sc);
   }
 }
@@ -171,19 +180,24 @@ __global__ void __launch_bounds__(256) gen_pupil_update(const GeneralParams p) {
     atomicMax(reinterpret_cast<unsigned*>(p.scal + (size_t)tile * 4 + 0), __float_as_uint(m));
 }
 
-// uint16 -> 1/I, natural order (the general path's stack layout)
-__global__ void __launch_bounds__(256) stack_convert_general(float* stack, const uint16_t* raw, long long first_elem, long long n) {
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
-    stack[first_elem + t] = 1.0f / (float)raw[first_elem + t];
+// uint16 -> 1/I (0 -> +inf: rsqrt(inf) = 0 = sqrt(0))
+__global__ void __launch_bounds__(256) stack_convert_general(float* stack, const uint16_t* raw, long long first_elem, long long n,
+                                                             int N, int R1) {
+  const int NN = N * N;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = first_elem + t, img = e / NN;
+    const int rem = (int)(e - img * NN);
+    stack[img * NN + stack_pos_offset(rem / N, rem % N, N, R1)] = 1.0f / (float)raw[e];
+  }
 }
 
-// sqrt(I) of the init slot -> complex scratch [tile][N][N]   (fpmMain.cpp:319-322), natural-order stack
-__global__ void gen_init_amp(float2* scratch, const float* stack, int n_leds, int slot, int tile0, int N) {
+// sqrt(I) of the init slot -> complex scratch [tile][N][N]   (fpmMain.cpp:319-322)
+__global__ void gen_init_amp(float2* scratch, const float* stack, int n_leds, int slot, int tile0, int N, int R1) {
   const int tile = tile0 + blockIdx.y;
   const float* img = stack + ((size_t)tile * n_leds + slot) * N * N;
   float2* out = scratch + (size_t)blockIdx.y * N * N;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N * N; t += gridDim.x * blockDim.x)
-    out[t] = make_float2(sqrtf(1.0f / img[t]), 0.f);
+    out[t] = make_float2(sqrtf(1.0f / img[stack_pos_offset(t / N, t % N, N, R1)]), 0.f);
 }
 
 }  // namespace fpm

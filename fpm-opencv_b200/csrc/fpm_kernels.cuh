@@ -8,6 +8,7 @@
 #include "fpm_update_cluster.cuh"
 #include "fpm_general.cuh"
 #include "fpm_general_fused.cuh"
+#include "fpm_pruned_fused.cuh"
 #include "fpm_fov.cuh"
 
 namespace fpm {

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <type_traits>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -16,6 +17,13 @@
 #include "fpm_kernels.cuh"
 
 using namespace fpm;
+
+// threads per CTA of fpm_update_pruned_kernel: 17 warps -- the 53 box rows of the shipped Np = 200 give 530 and 1060
+// work items per row stage (1 and 2 full rounds of 544), 50-column batches 500 and 1000
+#ifndef FPM_PRUNED_NT
+#define FPM_PRUNED_NT 544
+#endif
+static constexpr int PRUNED_NT = FPM_PRUNED_NT;
 
 static thread_local std::string g_err;
 
@@ -69,6 +77,9 @@ struct fpmb200_ctx {
   // general (unfused) path for tile sizes other than 64/128/256
   bool general = false;
   bool gfused = false;         // general sizes whose field fits shared memory twice: fpm_update_general_kernel
+  bool gpruned = false;        // general sizes with a compiled R1 x R2 plan whose pupil box fits: fpm_update_pruned_kernel
+  int stack_r1 = 0;            // stack layout of the general path (stack_pos_offset): 0 natural, else R1 of the pruned plan
+  int cb = 0;                  // columns per batch of fpm_update_pruned_kernel
   float2* gfield = nullptr;    // [n_tiles][N][N]
   float2* gq = nullptr;        // [n_tiles][N][N]
   float* gcells = nullptr;     // [n_tiles][cgr][cgc]
@@ -95,6 +106,7 @@ struct fpmb200_ctx {
 static int select_variant(fpmb200_ctx* c);
 static void factorize(int n, fpm::LineFFTParams& p);
 static int general_fused_plan(int N);
+static int pruned_plan(int N);
 
 extern "C" const char* fpmb200_last_error(void) { return g_err.c_str(); }
 extern "C" int fpmb200_abi_version(void) { return 1; }
@@ -207,11 +219,14 @@ extern "C" int fpmb200_tiles_alloc(fpmb200_ctx* c, int n_tiles, int Np, int Nlar
   if (Nlarge < Np || Nlarge > 3584 || (Nlarge & 1) || !smooth235(Nlarge))
     return fail(FPMB200_ERR_ARG, "Nlarge=%d must be even, in [Np, 3584], with prime factors 2,3,5 only", Nlarge);
   // the fused kernels need power-of-two tiles and 64-aligned spectra; everything else takes the general path
-  const bool general = !((Np == 64 || Np == 128 || Np == 256) && Nlarge % 64 == 0);
+  // (FPMB200_FORCE_GENERAL=1: developer switch, power-of-two tiles through the general-path kernels)
+  const char* fg = getenv("FPMB200_FORCE_GENERAL");
+  const bool general = !((Np == 64 || Np == 128 || Np == 256) && Nlarge % 64 == 0) || (fg && fg[0] == '1');
   CK(cudaSetDevice(c->device));
   free_tiles(c);
   c->N = Np; c->L = Nlarge; c->n_leds = n_leds;
   c->general = general;
+  c->stack_r1 = general ? pruned_plan(Np) / 100 : 0;       // the stack layout depends on Np only, never on the support
   // n_tiles is published only when every buffer exists: a failed allocation leaves an unallocated context
   const int rc = tiles_alloc_impl(c, n_tiles, Np, Nlarge, n_leds);
   if (rc != FPMB200_OK) {
@@ -356,6 +371,38 @@ static int select_variant(fpmb200_ctx* c) {
                "Np=%d Nlarge=%d maxcell=16x16 smem=%zuB", radices, N, c->L, c->smem_bytes);
       return FPMB200_OK;
     }
+    // Larger tiles with a compiled R1 x R2 plan (the shipped 200 = 20 x 10): the field is never materialised -- box rows
+    // in shared memory, columns in batches (fpm_pruned_fused.cuh); FPMB200_GENERAL_UNFUSED=1 keeps the per-step kernels
+    c->gpruned = false;
+    if (const int plan = pruned_plan(N)) {
+      const char* e = getenv("FPMB200_GENERAL_UNFUSED");
+      const int R1 = plan / 100, R2 = plan % 100, NT = PRUNED_NT;
+      const int nrb = c->yhi - c->ylo + 1;
+      const size_t base = pruned_fused_smem_bytes(N, nrb, 0, c->cgr, c->cgc);
+      const long long room = (long long)c->max_smem_optin - (long long)base;
+      const int cbmax = room > 0 ? (int)std::min<long long>(room / ((long long)sizeof(float2) * N), N) : 0;
+      if (cbmax >= 8 && !(e && e[0] == '1')) {
+        // columns per batch: whole rounds of NT work items in the three stages of a batch, few batches
+        auto rounds = [&](int items) { return (items + NT - 1) / NT; };
+        const double c1 = R1 * log2((double)R1), c2 = R2 * log2((double)R2);
+        double best = 1e300;
+        for (int cb = 8; cb <= cbmax; ++cb) {
+          double cost = 0;
+          for (int c0 = 0; c0 < N; c0 += cb) {
+            const int n = std::min(cb, N - c0);
+            cost += 2 * rounds(n * R2) * c1 + 2 * rounds(n * R1) * c2 + 0.5 * (c1 + c2);     // + barrier / ramp cost per batch
+          }
+          if (cost <= best) { best = cost; c->cb = cb; }
+        }
+        c->gpruned = true;
+        c->smem_bytes = pruned_fused_smem_bytes(N, nrb, c->cb, c->cgr, c->cgc);
+        snprintf(c->variant, sizeof c->variant,
+                 "general path, fused: fpm_update_pruned_kernel (one CTA per tile, box rows + %d-column batches in shared "
+                 "memory, radix %d x %d in place) Np=%d Nlarge=%d bbox=[%d..%d]x[%d..%d] maxcell=16x16 smem=%zuB",
+                 c->cb, R1, R2, N, c->L, ylo, yhi, xlo, xhi, c->smem_bytes);
+        return FPMB200_OK;
+      }
+    }
     if (!c->gfield) {
       const size_t NN = (size_t)N * N;
       CK(cudaMalloc(&c->gfield, sizeof(float2) * NN * c->n_tiles));
@@ -468,7 +515,8 @@ extern "C" int fpmb200_upload_stack(fpmb200_ctx* c, int first, int n, const uint
   const int n_img = n * c->n_leds;
   if (c->general) {
     const long long n_el = (long long)n_img * c->N * c->N;
-    stack_convert_general<<<(int)((n_el + 256 * 8 - 1) / (256 * 8)), 256, 0, st>>>(c->stack, c->raw, first_img * c->N * c->N, n_el);
+    stack_convert_general<<<(int)((n_el + 256 * 8 - 1) / (256 * 8)), 256, 0, st>>>(c->stack, c->raw, first_img * c->N * c->N, n_el,
+                                                                                    c->N, c->stack_r1);
   } else switch (c->N) {
     case 64: stack_convert_kernel<64><<<dim3(n_img, 64 / ConvertShape<64>::RB), 256, 0, st>>>(c->stack, c->raw, first_img); break;
     case 128: stack_convert_kernel<128><<<dim3(n_img, 128 / ConvertShape<128>::RB), 256, 0, st>>>(c->stack, c->raw, first_img); break;
@@ -531,7 +579,7 @@ extern "C" int fpmb200_init_tiles(fpmb200_ctx* c, int first, int n, int init_slo
   const int batch_max = (int)(c->scratch_elems / ((size_t)N * N));
   for (int t0 = first; t0 < first + n; t0 += batch_max) {
     const int b = (first + n - t0) < batch_max ? (first + n - t0) : batch_max;
-    if (c->general) gen_init_amp<<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0, N);
+    if (c->general) gen_init_amp<<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0, N, c->stack_r1);
     else switch (N) {
       case 64: init_amp_kernel<64><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
       case 128: init_amp_kernel<128><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
@@ -589,6 +637,7 @@ static void drop_graphs(fpmb200_ctx* c) {
 #endif
 static constexpr int GEN_NT = FPM_GEN_NT;
 
+
 // R1 * 100 + R2 of the compiled two-stage plan for Np, 0 if there is none
 static int general_fused_plan(int N) {
   const char* e = getenv("FPMB200_GENERAL_PLAN");
@@ -639,8 +688,49 @@ static int run_updates_general_fused(fpmb200_ctx* c, int first, int n, int slot_
   return FPMB200_OK;
 }
 
+// R1 * 100 + R2 of the compiled in-place plan of fpm_update_pruned_kernel for Np, 0 if there is none
+static int pruned_plan(int N) {
+  switch (N) {
+    case 200: return 2010;      // dataset_dogStomach.json as shipped
+    case 160: return 1610;
+    case 240: return 2012;
+    case 300: return 2015;
+    case 128: return 1608;      // only reachable with FPMB200_FORCE_GENERAL=1
+    default: return 0;
+  }
+}
+
+static int run_updates_pruned(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
+  PrunedParams p;
+  memset(&p, 0, sizeof p);
+  p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop; p.tw = c->twN;
+  p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first; p.slot_begin = slot_begin; p.n_updates = n_updates;
+  p.cgr = c->cgr; p.cgc = c->cgc; p.cb = c->cb;
+  p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi;
+  p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
+#ifdef FPM_STAGE_TIMING
+  if (!c->stage_clk) { CK(cudaMalloc(&c->stage_clk, 16 * sizeof(long long))); CK(cudaMemset(c->stage_clk, 0, 16 * sizeof(long long))); }
+  p.stage_clk = c->stage_clk;
+#endif
+  void (*k)(const PrunedParams) = nullptr;
+  switch (pruned_plan(c->N)) {
+    case 2010: k = fpm_update_pruned_kernel<PRUNED_NT, 20, 10>; break;
+    case 1610: k = fpm_update_pruned_kernel<PRUNED_NT, 16, 10>; break;
+    case 2012: k = fpm_update_pruned_kernel<PRUNED_NT, 20, 12>; break;
+    case 2015: k = fpm_update_pruned_kernel<PRUNED_NT, 20, 15>; break;
+    case 1608: k = fpm_update_pruned_kernel<PRUNED_NT, 16, 8>; break;
+    default: return fail(FPMB200_ERR_STATE, "no pruned plan for Np=%d", c->N);
+  }
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  k<<<n, PRUNED_NT, c->smem_bytes, st>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  return FPMB200_OK;
+}
+
 static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
   if (c->gfused) return run_updates_general_fused(c, first, n, slot_begin, n_updates, st);
+  if (c->gpruned) return run_updates_pruned(c, first, n, slot_begin, n_updates, st);
   GeneralParams p;
   memset(&p, 0, sizeof p);
   const int N = c->N;
@@ -648,6 +738,7 @@ static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin,
   p.field = c->gfield; p.q = c->gq; p.cells = c->gcells; p.scal = c->gscal;
   p.N = N; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first; p.cgr = c->cgr; p.cgc = c->cgc;
   p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
+  p.stack_r1 = c->stack_r1;
   // bounding box of the pupil support: P, Q and the object increment vanish outside it
   p.ylo = c->ylo; p.xlo = c->xlo; p.nrb = c->yhi - c->ylo + 1; p.ncb = c->xhi - c->xlo + 1;
   const int row0 = c->ylo < 0 ? c->ylo + N : c->ylo, col0 = c->xlo < 0 ? c->xlo + N : c->xlo;
@@ -881,10 +972,10 @@ extern "C" int fpmb200_ingest_frame(fpmb200_ctx* c, int led_slot, const uint16_t
   }
   CK(cudaMemcpyAsync(c->frame_dev, frame, sizeof(uint16_t) * elems, cudaMemcpyHostToDevice, st));
   ingest_bg_kernel<<<1, 1024, 0, st>>>(c->frame_dev, width, Np, bk1x, bk1y, bk2x, bk2y, bg_threshold, c->bg_dev + led_slot);
-  const int R1 = c->general ? 1 : (Np == 64 ? 8 : 16);
+  const int R1 = c->general ? (c->stack_r1 ? c->stack_r1 : 1) : (Np == 64 ? 8 : 16);
   const int bx = (Np * Np + 255) / 256 < 16 ? (Np * Np + 255) / 256 : 16;
   ingest_tiles_kernel<<<dim3(bx, c->n_tiles), 256, 0, st>>>(c->frame_dev, width, c->origins, 0, c->raw, c->stack, c->n_leds,
-                                                             led_slot, Np, R1, c->general ? 0 : 1, divisor, c->bg_dev + led_slot);
+                                                             led_slot, Np, R1, c->general ? (c->stack_r1 ? 2 : 0) : 1, divisor, c->bg_dev + led_slot);
   c->launches += 2;
   CK(cudaGetLastError());
   c->have_stack = true;

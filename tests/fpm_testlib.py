@@ -68,10 +68,10 @@ class SyntheticCase(Case):
     """A tile size no shipped JSON uses: Np and Nlarge chosen freely, windows on a seeded spiral around the centre
     (brightfield first, like the NA-sorted order of the reference); parameters of cfg7."""
 
-    def __init__(self, N, factor, seed, n_leds):
+    def __init__(self, N, factor, seed, n_leds, r=None):
         j = orc.load_json_lenient(embedded_path("cfg7_mono_np90"))
         self.name, self.cfg = "synthetic_np%d" % N, orc.config_from_json(j)
-        self.N, self.L, self.r = N, N * factor, max(3, N // 6)
+        self.N, self.L, self.r = N, N * factor, max(3, N // 6) if r is None else r
         rng = np.random.default_rng(seed)
         c0 = (self.L - N) // 2
         k = np.arange(n_leds)

@@ -234,6 +234,35 @@ def test_general_fused_other_sizes(N, factor, expect):
     ctx.close()
 
 
+@pytest.mark.parametrize("N,factor,r,expect", [(160, 3, 20, "radix 16 x 10"), (240, 2, 22, "radix 20 x 12"), (300, 2, 18, "radix 20 x 15"),
+                                               (200, 3, 40, "radix 20 x 10"), (128, 3, 17, "radix 16 x 8")])
+def test_pruned_fused_other_sizes(N, factor, r, expect, monkeypatch):
+    """Every compiled plan of fpm_update_pruned_kernel (box rows + column batches in shared memory) besides the shipped
+    Np = 200 case: per-step and full-run parity on synthetic geometry; Np = 128 reaches it through the developer switch
+    that sends power-of-two tiles down the general path."""
+    if N == 128:
+        monkeypatch.setenv("FPMB200_FORCE_GENERAL", "1")
+    c = T.SyntheticCase(N, factor, 100 + N, 16, r=r)
+    ctx = c.make_ctx()
+    assert "fpm_update_pruned_kernel" in ctx.variant and expect in ctx.variant, ctx.variant
+    st = orc.init_state(c.stack, c.L, c.r)
+    gF, _, gP = ctx.download(0, objCrop=False)
+    assert orc.rel_l2(gF, T.corner(st.objFc)) < 1e-6
+    for k in range(len(c.cx)):
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+    for k in range(5):
+        ctx.upload_state(0, T.corner(st.objFc), st.P)
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+        ctx.step(0, k)
+        compare(ctx, st, tol=STEP_TOL, crop=False)
+    ctx.init_tiles()
+    ctx.run(2)
+    ctx.finalize()
+    e = compare(ctx, c.oracle_run(2))
+    note("pruned fused Np=%d: 2 iterations x 16 LEDs rel-L2 objF %.2e pupil %.2e [%s]" % (N, e[0], e[1], ctx.variant[:110]))
+    ctx.close()
+
+
 def test_general_fused_variants_agree(monkeypatch):
     """Np = 90: the two-stage plan, the run-time radices and the unfused per-step kernels are three implementations of
     the same update; each within the full-run tolerance of the oracle (checked against one oracle run)."""
@@ -357,7 +386,8 @@ def test_dense_support_uses_general_path():
 @pytest.mark.parametrize("name,ell,unfused", [("cfg1_mono_np64", (3, 14.0, -5, 9.0), 0), ("cfg7_mono_np90", (3, 14.0, -5, 9.0), 0),
                                               ("cfg7_mono_np90", (20, 9.0, 12, 6.0), 0), ("cfg8_cellScope_np100", (-24, 11.0, 0, 30.0), 0),
                                               ("cfg7_mono_np90", (3, 14.0, -5, 9.0), 1), ("cfg7_mono_np90", (20, 9.0, 12, 6.0), 1),
-                                              ("cfg4s_dogStomach_np200", (-60, 25.0, 33, 40.0), 0)])
+                                              ("cfg4s_dogStomach_np200", (-60, 25.0, 33, 40.0), 0), ("cfg4s_dogStomach_np200", (-60, 25.0, 33, 40.0), 1),
+                                              ("cfg4s_dogStomach_np200", (5, 30.0, -9, 12.0), 0)])
 def test_asymmetric_support_bbox(name, ell, unfused, monkeypatch):
     """An off-centre elliptical support exercises the wrapped bbox arithmetic (fused power-of-two kernel, the fused
     general kernel and the unfused general path; boxes that straddle the origin or lie on one side of it)."""
@@ -640,13 +670,13 @@ def test_full_size_oracle_parity(name, iters):
         ctx.close()
 
 
-def test_support_reupload_rebuilds_the_unfused_graph():
+def test_support_reupload_rebuilds_the_unfused_graph(monkeypatch):
     """Np = 200 replays a captured CUDA graph per pass over the LEDs; the graph bakes in the bounding box of the pupil
     support.  Uploading another support on the same context must not replay the old one."""
+    monkeypatch.setenv("FPMB200_GENERAL_UNFUSED", "1")
     c = T.Case("cfg4s_dogStomach_np200", 4, 10)
     ctx = c.make_ctx()
-    if "unfused" not in ctx.variant:
-        pytest.skip("Np=200 no longer takes the graph-replayed path: " + ctx.variant)
+    assert "unfused" in ctx.variant
     ctx.run(1)
     N = c.N
     y, x = np.mgrid[0:N, 0:N]

@@ -20,6 +20,15 @@ for name in names:
         n_upd = 2 * len(c.cx)
         v = np.array(list(buf), dtype=np.float64) / n_upd
         labels = ["-", "S1 colA(inv)+O*P", "S2 colB(inv)", "S3 rowA(inv)", "S4 rowB+amp+rowB'", "S5 rowA'", "S6 colB'", "S7 colA'", "C2 object update", "D max|objF|", "E pupil+next window"]
+        if "fpm_update_pruned_kernel" in ctx.variant:
+            print(name, "tiles", n_tiles, ctx.variant)
+            for k, lab in enumerate(["-", "A P+=Q, O*P (box)", "IR-A inv rows A", "IR-B inv rows B", "IC-A inv cols A (X->S)", "MID inv B + amp + fwd B'",
+                                     "FC-A' fwd cols A' (S->X)", "FR-B' fwd rows B'", "FR-A' fwd rows A'", "C object/pupil incr.", "D cell rebuild", "D grid scan"]):
+                if k:
+                    print("   %-28s %8.0f cyc  %5.1f%%" % (lab, v[k], 100 * v[k] / v[1:16].sum()))
+            print("   total %.0f cycles/update" % v[1:16].sum())
+            ctx.close()
+            continue
         if "general path, fused" in ctx.variant:
             # ticks of fpm_update_general_kernel: 11 = A's element loop, 1 = its barrier + max|P|; 14 = C; 12 = D's cell
             # rebuild, 13 = its barrier, 10 = the grid scan
