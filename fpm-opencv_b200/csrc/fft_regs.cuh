@@ -54,6 +54,16 @@ __host__ __device__ __forceinline__ float2 cscale(float2 a, float s) {
   return make_float2(a.x * s, a.y * s);
 #endif
 }
+// s * a + b (real scalar s): one packed FFMA2 with the scalar broadcast to both halves
+__host__ __device__ __forceinline__ float2 cfma(float s, float2 a, float2 b) {
+#if FPM_PACKED
+  return __ffma2_rn(make_float2(s, s), a, b);
+#else
+  return make_float2(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y));
+#endif
+}
+// multiply by +i
+__host__ __device__ __forceinline__ float2 muli(float2 a) { return make_float2(-a.y, a.x); }
 // multiply by -i (forward quarter turn) or +i (inverse)
 template <bool INV> __host__ __device__ __forceinline__ float2 rot90(float2 a) {
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
@@ -89,26 +99,27 @@ template <bool INV> __host__ __device__ __forceinline__ void fft4(float2& x0, fl
 
 template <bool INV> __host__ __device__ __forceinline__ void fft3(float2& x0, float2& x1, float2& x2) {
   const float s = INV ? 0.86602540378443864676f : -0.86602540378443864676f;   // Im(W3)
-  float2 t1 = cadd(x1, x2);
-  float2 t2 = make_float2(fmaf(-0.5f, t1.x, x0.x), fmaf(-0.5f, t1.y, x0.y));
-  float2 d = csub(x1, x2);
-  float2 t3 = make_float2(-s * d.y, s * d.x);      // i*s*d
+  const float2 t1 = cadd(x1, x2);
+  const float2 t2 = cfma(-0.5f, t1, x0);
+  const float2 t3 = muli(cscale(csub(x1, x2), s));      // i*s*d
   x0 = cadd(x0, t1);
   x1 = cadd(t2, t3);
   x2 = csub(t2, t3);
 }
 
+// packed form (FADD2 / FFMA2 / FMUL2 on whole complex values: 20 instructions instead of ~40 scalar ones; the stages of
+// the mixed-radix kernels are issue-bound on exactly these butterflies)
 template <bool INV> __host__ __device__ __forceinline__ void fft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
   const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;    // cos(2pi/5), cos(4pi/5)
   const float s1 = INV ? 0.95105651629515357212f : -0.95105651629515357212f;  // +-sin(2pi/5)
   const float s2 = INV ? 0.58778525229247312917f : -0.58778525229247312917f;  // +-sin(4pi/5)
-  float2 a1 = cadd(x1, x4), b1 = csub(x1, x4), a2 = cadd(x2, x3), b2 = csub(x2, x3);
-  float2 y0 = cadd(x0, cadd(a1, a2));
-  float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
-  float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
+  const float2 a1 = cadd(x1, x4), b1 = csub(x1, x4), a2 = cadd(x2, x3), b2 = csub(x2, x3);
+  const float2 y0 = cadd(x0, cadd(a1, a2));
+  const float2 p1 = cfma(c1, a1, cfma(c2, a2, x0));
+  const float2 p2 = cfma(c2, a1, cfma(c1, a2, x0));
   // q = i*(s1*b1 + s2*b2),  r = i*(s2*b1 - s1*b2)
-  float2 q = make_float2(-(s1 * b1.y + s2 * b2.y), s1 * b1.x + s2 * b2.x);
-  float2 r = make_float2(-(s2 * b1.y - s1 * b2.y), s2 * b1.x - s1 * b2.x);
+  const float2 q = muli(cfma(s1, b1, cscale(b2, s2)));
+  const float2 r = muli(cfma(s2, b1, cscale(b2, -s1)));
   x0 = y0;
   x1 = cadd(p1, q);
   x4 = csub(p1, q);
@@ -341,6 +352,69 @@ template <int R, bool INV> __host__ __device__ __forceinline__ void fft_reg(floa
     // ... then for every k1 a B-point transform over b: slot B*k1 + k2 = X[k1 + A*k2]
     static_for<0, A>([&](auto K1) { fft_strided<B, INV, B * decltype(K1)::value, 1>(v); });
   }
+}
+
+// ---- pruned butterflies for R = 4 * B (radix 20 of the Np = 200 plan) -------------------------------------------------
+// Input pruning: only x[0], x[1], x[2], x[R-3], x[R-2], x[R-1] are non-zero (w = those six, in that order) -- the
+// samples of a line that lie inside a narrow pupil box.  The first layer (4-point transforms over a, n = B*a + b)
+// sees at most the entries a = 0 and a = 3 and degenerates to copies / one addition; the result equals fft_reg<R> of
+// the zero-padded input up to the sign of exact zeros.  Same slot convention as fft_reg<R>.
+template <int R, bool INV> __host__ __device__ __forceinline__ void fft_reg_in6(const float2 (&w)[6], float2 (&v)[R]) {
+  constexpr int A = RadixSplit<R>::A, B = RadixSplit<R>::B;
+  static_assert(A == 4 && B >= 3 && B <= 6, "fft_reg_in6: R = 4 * B, 3 <= B <= 6");
+  static_for<0, B>([&](auto Bq) {
+    constexpr int b = decltype(Bq)::value;
+    constexpr bool has_lo = b <= 2, has_hi = b >= B - 3;
+    if constexpr (has_lo && has_hi) {
+      const float2 lo = w[b], hi = w[3 + b - (B - 3)], r = rot90<INV>(hi);
+      v[b] = cadd(lo, hi); v[B + b] = csub(lo, r); v[2 * B + b] = csub(lo, hi); v[3 * B + b] = cadd(lo, r);
+    } else if constexpr (has_lo) {
+      const float2 lo = w[b];
+      v[b] = lo; v[B + b] = lo; v[2 * B + b] = lo; v[3 * B + b] = lo;
+    } else {
+      const float2 hi = w[3 + b - (B - 3)], r = rot90<INV>(hi);
+      v[b] = hi; v[B + b] = make_float2(-r.x, -r.y); v[2 * B + b] = make_float2(-hi.x, -hi.y); v[3 * B + b] = r;
+    }
+  });
+  static_for<1, A>([&](auto K1) {
+    static_for<1, B>([&](auto Bq) {
+      constexpr int k1 = decltype(K1)::value, b = decltype(Bq)::value;
+      constexpr float c = (float)cx_cos(root_angle(k1 * b, R)), s = (float)cx_sin(root_angle(k1 * b, R));
+      v[B * k1 + b] = twmul<INV>(v[B * k1 + b], make_float2(c, -s));
+    });
+  });
+  static_for<0, A>([&](auto K1) { fft_strided<B, INV, B * decltype(K1)::value, 1>(v); });
+}
+
+// Output pruning (R = 20): only X[0], X[1], X[2], X[R-3], X[R-2], X[R-1] are wanted (o = those six, in that order) --
+// the samples of a transformed line inside a narrow pupil box.  X[k1 + 4*k2]: the last layer (5-point transforms over
+// b for every k1) is asked for k2 = 0 (k1 = 0, 1, 2) and k2 = 4 (k1 = 1, 2, 3) only.
+template <int R, bool INV> __host__ __device__ __forceinline__ void fft_reg_out6(float2 (&v)[R], float2 (&o)[6]) {
+  constexpr int A = RadixSplit<R>::A, B = RadixSplit<R>::B;
+  static_assert(A == 4 && B == 5, "fft_reg_out6: R = 20");
+  static_for<0, B>([&](auto Bq) { fft_strided<A, INV, decltype(Bq)::value, B>(v); });
+  static_for<1, A>([&](auto K1) {
+    static_for<1, B>([&](auto Bq) {
+      constexpr int k1 = decltype(K1)::value, b = decltype(Bq)::value;
+      constexpr float c = (float)cx_cos(root_angle(k1 * b, R)), s = (float)cx_sin(root_angle(k1 * b, R));
+      v[B * k1 + b] = twmul<INV>(v[B * k1 + b], make_float2(c, -s));
+    });
+  });
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;    // cos(2pi/5), cos(4pi/5)
+  const float s1 = INV ? 0.95105651629515357212f : -0.95105651629515357212f;  // +-sin(2pi/5)
+  const float s2 = INV ? 0.58778525229247312917f : -0.58778525229247312917f;  // +-sin(4pi/5)
+  static_for<0, A>([&](auto K1) {
+    constexpr int k1 = decltype(K1)::value;
+    const float2 y0 = v[B * k1], y1 = v[B * k1 + 1], y2 = v[B * k1 + 2], y3 = v[B * k1 + 3], y4 = v[B * k1 + 4];
+    const float2 a1 = cadd(y1, y4), a2 = cadd(y2, y3);
+    if constexpr (k1 <= 2) o[k1] = cadd(y0, cadd(a1, a2));                                   // k2 = 0
+    if constexpr (k1 >= 1) {                                                                 // k2 = 4: p1 - q of fft5
+      const float2 b1 = csub(y1, y4), b2 = csub(y2, y3);
+      const float2 p1 = cfma(c1, a1, cfma(c2, a2, y0));
+      const float2 q = muli(cfma(s1, b1, cscale(b2, s2)));
+      o[2 + k1] = csub(p1, q);
+    }
+  });
 }
 
 }  // namespace fpm

@@ -55,6 +55,12 @@ __host__ __device__ inline size_t pruned_fused_smem_bytes(int N, int nrb, int cb
   return sizeof(float2) * ((size_t)nrb * (N + 1) + (size_t)N * cb + N) + sizeof(float) * ((size_t)cgr * cgc + 64) + 64;
 }
 
+#ifndef FPM_PRUNED_ILP
+#define FPM_PRUNED_ILP 1      // work items per thread in flight in the B / B' / MID stages.  Measured on B200 (Np = 200, 148
+                              // tiles): 2 items in flight spill at the 96-register cap of 17-20 warps and lose 15-20 %
+                              // (640 threads: 4.62 M updates/s with 1, 3.59 M with 2; 512 threads: 4.44 M / 4.06 M)
+#endif
+
 template <int N> __device__ __forceinline__ int wrap_half_c(int i) { return (i < N / 2) ? i : i - N; }
 
 // One in-place stage of the two-stage transforms over `nl` lines (lanes run over lines: element stride es, line
@@ -69,7 +75,12 @@ template <int N> __device__ __forceinline__ int wrap_half_c(int i) { return (i <
 //           where the wrapped index lies in [z0, z0+nz); ZDST: compacted (index - z0)
 //   KIND 4  KIND 1 + amplitude replacement + KIND 2 on the same registers (the middle of the column phase);
 //           inv_i points at the 1/I row of line 0: element (position row r, line li) at inv_i[r * N + li]
-template <int NT, int R1, int R2, int KIND, bool ZSRC, bool ZDST>
+// NARROW (R1 = 20): the box [z0, z0+nz) lies within +-3*R2 of the origin, so a stage-A butterfly has at most the six
+// samples n1 = 0, 1, 2, R1-3, R1-2, R1-1 inside it: KIND 0 loads those six (unconditionally, clamped + masked) and
+// runs fft_reg_in6, KIND 3 computes those six outputs only (fft_reg_out6).
+// Stages B / B' / MID can run two work items per thread at a time (FPM_PRUNED_ILP = 2: loads issued together, two
+// independent butterfly streams); off by default, see above.
+template <int NT, int R1, int R2, int KIND, bool ZSRC, bool ZDST, bool NARROW>
 __device__ __forceinline__ void pruned_stage(const float2* __restrict__ src, float2* __restrict__ dst,
                                              const float2* __restrict__ tws, int es_src, int es_dst, int ls, int tid, int nl,
                                              int z0, int nz, const float* __restrict__ inv_i, float epsr, float epsi) {
@@ -81,77 +92,131 @@ __device__ __forceinline__ void pruned_stage(const float2* __restrict__ src, flo
   const int total = nl * J;
   const int qNT = NT / nl, rNT = NT % nl;
   int j = tid / nl, li = tid % nl;
-  for (int t = tid; t < total; t += NT) {
-    float2 v[R];
-    if constexpr (KIND == 0) {
-      const float2* s = src + li * ls;
+  auto advance = [&](int& jj, int& ll) { jj += qNT; ll += rNT; if (ll >= nl) { ll -= nl; ++jj; } };
+  if constexpr (STAGE_A) {
+    for (int t = tid; t < total; t += NT) {
+      float2 v[R];
+      if constexpr (KIND == 0) {
+        const float2* s = src + li * ls;
+        if constexpr (NARROW) {
+          float2 w6[6];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int w = wrap_half_c<N>(j + R2 * r) - z0;
-        v[r] = make_float2(0.f, 0.f);
-        if ((unsigned)w < (unsigned)nz) v[r] = s[(ZSRC ? w : j + R2 * r) * es_src];
+          for (int q = 0; q < 6; ++q) {
+            const int n1 = q < 3 ? q : R - 6 + q;
+            const int w = wrap_half_c<N>(j + R2 * n1) - z0;
+            const bool in = (unsigned)w < (unsigned)nz;
+            const float2 x = s[(ZSRC ? (in ? w : 0) : j + R2 * n1) * es_src];         // always a valid address
+            w6[q] = in ? x : make_float2(0.f, 0.f);
+          }
+          fft_reg_in6<R, INV>(w6, v);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int w = wrap_half_c<N>(j + R2 * r) - z0;
+            v[r] = make_float2(0.f, 0.f);
+            if ((unsigned)w < (unsigned)nz) v[r] = s[(ZSRC ? w : j + R2 * r) * es_src];
+          }
+          fft_reg<R, INV>(v);
+        }
+        float2* d = dst + li * ls + j * es_dst;
+        static_for<0, R>([&](auto I) {
+          constexpr int i = decltype(I)::value, k1 = radix_out<R>(i);
+          float2 val = v[i];
+          if constexpr (k1 > 0) val = twmul<INV>(val, tws[j * k1]);
+          d[R2 * k1 * es_dst] = val;
+        });
+      } else {                                          // KIND 3
+        const float2* s = src + li * ls + j * es_src;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = s[R2 * r * es_src];
+        float2* d = dst + li * ls;
+        if constexpr (NARROW) {
+          float2 o6[6];
+          fft_reg_out6<R, false>(v, o6);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const int q1 = q < 3 ? q : R - 6 + q;
+            const int w = wrap_half_c<N>(j + R2 * q1) - z0;
+            if ((unsigned)w < (unsigned)nz) d[(ZDST ? w : j + R2 * q1) * es_dst] = o6[q];
+          }
+        } else {
+          fft_reg<R, false>(v);
+          static_for<0, R>([&](auto I) {
+            constexpr int i = decltype(I)::value, q1 = radix_out<R>(i);
+            const int w = wrap_half_c<N>(j + R2 * q1) - z0;
+            if ((unsigned)w < (unsigned)nz) d[(ZDST ? w : j + R2 * q1) * es_dst] = v[i];
+          });
+        }
       }
-      fft_reg<R, INV>(v);
-      float2* d = dst + li * ls + j * es_dst;
-      static_for<0, R>([&](auto I) {
-        constexpr int i = decltype(I)::value, k1 = radix_out<R>(i);
-        float2 val = v[i];
-        if constexpr (k1 > 0) val = twmul<INV>(val, tws[j * k1]);
-        d[R2 * k1 * es_dst] = val;
-      });
-    } else if constexpr (KIND == 1 || KIND == 2) {
-      float2* d = dst + li * ls + R2 * j * es_dst;
-#pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = d[r * es_dst];
-      fft_reg<R, INV>(v);
-      static_for<0, R>([&](auto I) {
-        constexpr int i = decltype(I)::value, k2 = radix_out<R>(i);
-        float2 val = v[i];
-        if constexpr (KIND == 2 && k2 > 0) val = twmul<false>(val, tws[j * k2]);
-        d[k2 * es_dst] = val;
-      });
-    } else if constexpr (KIND == 4) {
-      float2* d = dst + li * ls + R2 * j * es_dst;
-      float ii[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) ii[r] = __ldg(inv_i + (R2 * j + r) * N + li);      // position row R2*k1 + k2, coalesced over li
-#pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = d[r * es_dst];
-      fft_reg<R, true>(v);
-      float2 w[R];
-      static_for<0, R>([&](auto I) {
-        constexpr int i = decltype(I)::value, k2 = radix_out<R>(i);
-        const float2 val = v[i];
-        const float2 tt = make_float2(val.x + epsr, val.y + epsi);
-        const float sc = rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y) * ii[k2]);          // sqrt(I)/|psi+eps|; I = 0 -> 0
-        w[k2] = make_float2(val.x * sc, val.y * sc);
-      });
-      fft_reg<R, false>(w);
-      static_for<0, R>([&](auto I) {
-        constexpr int i = decltype(I)::value, q2 = radix_out<R>(i);
-        float2 val = w[i];
-        if constexpr (q2 > 0) val = twmul<false>(val, tws[j * q2]);
-        d[q2 * es_dst] = val;
-      });
-    } else {                                          // KIND 3
-      const float2* s = src + li * ls + j * es_src;
-#pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = s[R2 * r * es_src];
-      fft_reg<R, false>(v);
-      float2* d = dst + li * ls;
-      static_for<0, R>([&](auto I) {
-        constexpr int i = decltype(I)::value, q1 = radix_out<R>(i);
-        const int w = wrap_half_c<N>(j + R2 * q1) - z0;
-        if ((unsigned)w < (unsigned)nz) d[(ZDST ? w : j + R2 * q1) * es_dst] = v[i];
-      });
+      advance(j, li);
     }
-    j += qNT; li += rNT;
-    if (li >= nl) { li -= nl; ++j; }
+  } else {
+    // two items per thread in flight: (j, li) and the item NT further on
+    auto load = [&](int jj, int ll, float2 (&v)[R], float (&ii)[R]) {
+      const float2* d = dst + ll * ls + R2 * jj * es_dst;
+      if constexpr (KIND == 4) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) ii[r] = __ldg(inv_i + (R2 * jj + r) * N + ll);    // position row R2*k1 + k2, coalesced over lines
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = d[r * es_dst];
+    };
+    auto compute_store = [&](int jj, int ll, float2 (&v)[R], float (&ii)[R]) {
+      float2* d = dst + ll * ls + R2 * jj * es_dst;
+      fft_reg<R, INV>(v);
+      if constexpr (KIND == 4) {
+        float2 w[R];
+        static_for<0, R>([&](auto I) {
+          constexpr int i = decltype(I)::value, k2 = radix_out<R>(i);
+          const float2 val = v[i];
+          const float2 tt = make_float2(val.x + epsr, val.y + epsi);
+          const float sc = rsqrt_fast(fmaf(tt.x, tt.x, tt.y * tt.y) * ii[k2]);        // sqrt(I)/|psi+eps|; I = 0 -> 0
+          w[k2] = make_float2(val.x * sc, val.y * sc);
+        });
+        fft_reg<R, false>(w);
+        static_for<0, R>([&](auto I) {
+          constexpr int i = decltype(I)::value, q2 = radix_out<R>(i);
+          float2 val = w[i];
+          if constexpr (q2 > 0) val = twmul<false>(val, tws[jj * q2]);
+          d[q2 * es_dst] = val;
+        });
+      } else {
+        static_for<0, R>([&](auto I) {
+          constexpr int i = decltype(I)::value, k2 = radix_out<R>(i);
+          float2 val = v[i];
+          if constexpr (KIND == 2 && k2 > 0) val = twmul<false>(val, tws[jj * k2]);
+          d[k2 * es_dst] = val;
+        });
+      }
+    };
+    if constexpr (FPM_PRUNED_ILP == 2) {
+      for (int t = tid; t < total; t += 2 * NT) {
+        int j2 = j, li2 = li;
+        advance(j2, li2);
+        const bool two = t + NT < total;
+        float2 va[R], vb[R];
+        float ia[R], ib[R];
+        load(j, li, va, ia);
+        if (two) load(j2, li2, vb, ib);
+        compute_store(j, li, va, ia);
+        if (two) compute_store(j2, li2, vb, ib);
+        j = j2; li = li2;
+        advance(j, li);
+      }
+    } else {
+      for (int t = tid; t < total; t += NT) {
+        float2 va[R];
+        float ia[R];
+        load(j, li, va, ia);
+        compute_store(j, li, va, ia);
+        advance(j, li);
+      }
+    }
   }
   __syncthreads();
 }
 
-template <int NT, int R1, int R2>
+template <int NT, int R1, int R2, bool NARROW>
 __global__ void __launch_bounds__(NT, 1) fpm_update_pruned_kernel(const __grid_constant__ PrunedParams p) {
   constexpr int N = R1 * R2, H = N / 2, PX = N + 1, NN = N * N, NW = NT / 32;
   static_assert(NT % 32 == 0 && N % 2 == 0, "whole warps, even tile edge");
@@ -222,6 +287,13 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_pruned_kernel(const __grid_c
   for (int u = 0; u < p.n_updates; ++u) {
     const short2 cr = p.crop[slot];
     float2* O = objFc + (size_t)(cr.y + H) * L + (cr.x + H);           // window origin: wrapped indices -H .. H-1
+    // the next LED's 1/I image towards L2 while this update computes (the amplitude stage reads it with plain loads)
+    if (tid < 8 && u + 1 < p.n_updates) {
+      const int nslot = slot + 1 == p.n_leds ? 0 : slot + 1;
+      constexpr unsigned chunk = (unsigned)(NN * 4 / 8) & ~15u;        // eight pieces, 16-byte multiples (the tail is not prefetched)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(stack + (size_t)nslot * NN) + (size_t)tid * chunk),
+                   "r"(chunk) : "memory");
+    }
 
     // ---- A: (P += Q / max|objF|), Phi = O * P on the box -> X, max|P|^2 ----
     {
@@ -269,21 +341,21 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_pruned_kernel(const __grid_c
     FPM_TICK(1);
 
     // ---- IR: inverse rows of the box (lanes over rows: element stride 1, line stride PX) ----
-    pruned_stage<NT, R1, R2, 0, false, false>(X, X, tws, 1, 1, PX, tid, NRb, p.xlo, NCb, nullptr, 0.f, 0.f); FPM_TICK(2);
-    pruned_stage<NT, R1, R2, 1, false, false>(X, X, tws, 1, 1, PX, tid, NRb, 0, 0, nullptr, 0.f, 0.f); FPM_TICK(3);
+    pruned_stage<NT, R1, R2, 0, false, false, NARROW>(X, X, tws, 1, 1, PX, tid, NRb, p.xlo, NCb, nullptr, 0.f, 0.f); FPM_TICK(2);
+    pruned_stage<NT, R1, R2, 1, false, false, NARROW>(X, X, tws, 1, 1, PX, tid, NRb, 0, 0, nullptr, 0.f, 0.f); FPM_TICK(3);
 
     // ---- column phase, CB column positions at a time (lanes over columns: line stride 1) ----
     const float* __restrict__ inv_led = stack + (size_t)slot * NN;
     for (int c0 = 0; c0 < N; c0 += CB) {
       const int ncb = min(CB, N - c0);
-      pruned_stage<NT, R1, R2, 0, true, false>(X + c0, S, tws, PX, CB, 1, tid, ncb, p.ylo, NRb, nullptr, 0.f, 0.f); FPM_TICK(4);
-      pruned_stage<NT, R1, R2, 4, false, false>(S, S, tws, CB, CB, 1, tid, ncb, 0, 0, inv_led + c0, epsr, epsi); FPM_TICK(5);
-      pruned_stage<NT, R1, R2, 3, false, true>(S, X + c0, tws, CB, PX, 1, tid, ncb, p.ylo, NRb, nullptr, 0.f, 0.f); FPM_TICK(6);
+      pruned_stage<NT, R1, R2, 0, true, false, NARROW>(X + c0, S, tws, PX, CB, 1, tid, ncb, p.ylo, NRb, nullptr, 0.f, 0.f); FPM_TICK(4);
+      pruned_stage<NT, R1, R2, 4, false, false, NARROW>(S, S, tws, CB, CB, 1, tid, ncb, 0, 0, inv_led + c0, epsr, epsi); FPM_TICK(5);
+      pruned_stage<NT, R1, R2, 3, false, true, NARROW>(S, X + c0, tws, CB, PX, 1, tid, ncb, p.ylo, NRb, nullptr, 0.f, 0.f); FPM_TICK(6);
     }
 
     // ---- FR: forward rows of the box, box columns kept ----
-    pruned_stage<NT, R1, R2, 2, false, false>(X, X, tws, 1, 1, PX, tid, NRb, 0, 0, nullptr, 0.f, 0.f); FPM_TICK(7);
-    pruned_stage<NT, R1, R2, 3, false, false>(X, X, tws, 1, 1, PX, tid, NRb, p.xlo, NCb, nullptr, 0.f, 0.f); FPM_TICK(8);
+    pruned_stage<NT, R1, R2, 2, false, false, NARROW>(X, X, tws, 1, 1, PX, tid, NRb, 0, 0, nullptr, 0.f, 0.f); FPM_TICK(7);
+    pruned_stage<NT, R1, R2, 3, false, false, NARROW>(X, X, tws, 1, 1, PX, tid, NRb, p.xlo, NCb, nullptr, 0.f, 0.f); FPM_TICK(8);
 
     // ---- C: object update (old pupil) written to the spectrum, Q from the old window in place of Phi' ----
     {

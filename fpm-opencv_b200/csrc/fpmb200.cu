@@ -18,10 +18,11 @@
 
 using namespace fpm;
 
-// threads per CTA of fpm_update_pruned_kernel: 17 warps -- the 53 box rows of the shipped Np = 200 give 530 and 1060
-// work items per row stage (1 and 2 full rounds of 544), 50-column batches 500 and 1000
+// threads per CTA of fpm_update_pruned_kernel: 20 warps (5 per scheduler, 96 registers).  The stages are a few rounds
+// of long dependent butterfly chains, i.e. latency-bound: measured at Np = 200 / 148 tiles, 512 threads 4.44 M
+// updates/s, 544: 4.29 M, 640: 4.62 M, 704 / 768 / 896 (80 / 80 / 72 registers, spills): 4.16 / 4.25 / 4.12 M.
 #ifndef FPM_PRUNED_NT
-#define FPM_PRUNED_NT 544
+#define FPM_PRUNED_NT 640
 #endif
 static constexpr int PRUNED_NT = FPM_PRUNED_NT;
 
@@ -395,11 +396,16 @@ static int select_variant(fpmb200_ctx* c) {
           if (cost <= best) { best = cost; c->cb = cb; }
         }
         c->gpruned = true;
+        {
+          const int lim = 3 * R2;
+          const char* en = getenv("FPMB200_PRUNED_NARROW");
+          c->narrow = R1 == 20 && ylo >= -lim && yhi <= lim - 1 && xlo >= -lim && xhi <= lim - 1 && !(en && en[0] == '0');
+        }
         c->smem_bytes = pruned_fused_smem_bytes(N, nrb, c->cb, c->cgr, c->cgc);
         snprintf(c->variant, sizeof c->variant,
                  "general path, fused: fpm_update_pruned_kernel (one CTA per tile, box rows + %d-column batches in shared "
-                 "memory, radix %d x %d in place) Np=%d Nlarge=%d bbox=[%d..%d]x[%d..%d] maxcell=16x16 smem=%zuB",
-                 c->cb, R1, R2, N, c->L, ylo, yhi, xlo, xhi, c->smem_bytes);
+                 "memory, radix %d x %d in place%s) Np=%d Nlarge=%d bbox=[%d..%d]x[%d..%d] maxcell=16x16 smem=%zuB",
+                 c->cb, R1, R2, c->narrow ? ", six-sample stage-A butterflies" : "", N, c->L, ylo, yhi, xlo, xhi, c->smem_bytes);
         return FPMB200_OK;
       }
     }
@@ -713,12 +719,13 @@ static int run_updates_pruned(fpmb200_ctx* c, int first, int n, int slot_begin, 
   p.stage_clk = c->stage_clk;
 #endif
   void (*k)(const PrunedParams) = nullptr;
+  const bool nw = c->narrow;      // the box lies within +-3*R2: six-sample butterflies in the stage-A passes (R1 = 20 plans)
   switch (pruned_plan(c->N)) {
-    case 2010: k = fpm_update_pruned_kernel<PRUNED_NT, 20, 10>; break;
-    case 1610: k = fpm_update_pruned_kernel<PRUNED_NT, 16, 10>; break;
-    case 2012: k = fpm_update_pruned_kernel<PRUNED_NT, 20, 12>; break;
-    case 2015: k = fpm_update_pruned_kernel<PRUNED_NT, 20, 15>; break;
-    case 1608: k = fpm_update_pruned_kernel<PRUNED_NT, 16, 8>; break;
+    case 2010: k = nw ? fpm_update_pruned_kernel<PRUNED_NT, 20, 10, true> : fpm_update_pruned_kernel<PRUNED_NT, 20, 10, false>; break;
+    case 1610: k = fpm_update_pruned_kernel<PRUNED_NT, 16, 10, false>; break;
+    case 2012: k = nw ? fpm_update_pruned_kernel<PRUNED_NT, 20, 12, true> : fpm_update_pruned_kernel<PRUNED_NT, 20, 12, false>; break;
+    case 2015: k = nw ? fpm_update_pruned_kernel<PRUNED_NT, 20, 15, true> : fpm_update_pruned_kernel<PRUNED_NT, 20, 15, false>; break;
+    case 1608: k = fpm_update_pruned_kernel<PRUNED_NT, 16, 8, false>; break;
     default: return fail(FPMB200_ERR_STATE, "no pruned plan for Np=%d", c->N);
   }
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
