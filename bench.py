@@ -74,7 +74,7 @@ def geometry(cfg_json=None):
     n = ds.geometry(1, min(293, s.ledCount) if cfg_json is None else s.ledCount)
     cx, cy = ds.crop_tables()
     return dict(N=s.Np, L=s.Nlarge, r=s.naRadius, n_leds=n, cx=cx, cy=cy, delta1=s.delta1, delta2=s.delta2, eps=s.eps,
-                support=fpmhost.pupil_support(s.Np, s.naRadius))
+                support=fpmhost.pupil_support(s.Np, s.naRadius), order=[int(v) for v in ds.order])
 
 
 def geometry_reference_arm(name="cfg4_dogStomach_np128"):
@@ -150,6 +150,75 @@ def measure_peaks(device):
         return {"error": repr(e)}
 
 
+def fov_e2e_leg(n_gpus, g, stacks, iters, W=2560, H=2160):
+    """Full-FOV reconstruction END TO END through the reference's entry point: `fpmMain <dataset.json> <itrCount>` with
+    FPM_FOV_OVERLAP=0 and FPM_GPUS=0..n-1 on a directory of synthetic 16-bit TIFF frames (one 2560x2160 frame per LED,
+    157 frames = 1.7 GB): directory scan + LED geometry, TIFF read, device-side tile cut, reconstruction of all 320
+    tiles, final gather and amplitude mosaic back in host memory.  Wall clock of the whole process (CUDA context creation
+    included) and fpmMain's own phase timing; two passes (the second reads the frames from the page cache)."""
+    import shutil
+    import tempfile
+    import synth
+    N, n_leds = g["N"], g["n_leds"]
+    need = n_leds * W * H * 2 * 1.1
+    root = None
+    for base in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            st = os.statvfs(base)
+            if st.f_bavail * st.f_frsize > need:
+                root = tempfile.mkdtemp(prefix="fpm_fov_", dir=base)
+                break
+        except OSError:
+            pass
+    if root is None:
+        return {"error": "no scratch directory with %.1f GB free for the synthetic frames" % (need / 1e9)}
+    try:
+        t0 = time.perf_counter()
+        nx, ny = W // N, H // N
+        idx = (np.arange(nx * ny) % len(stacks)).reshape(ny, nx)
+        st8 = np.stack(stacks)                                   # [8][n_leds][N][N]
+        frame = np.zeros((H, W), np.uint16)
+        for k, led in enumerate(g["order"]):
+            frame[:ny * N, :nx * N] = st8[idx, k].transpose(0, 2, 1, 3).reshape(ny * N, nx * N)
+            synth.write_tiff16(os.path.join(root, "ILED_%04d.tif" % led), frame)
+        j = json.load(open(CFG_JSON))
+        j.update(datasetRoot=root + "/", cropX=0, cropY=0, bk1cropX=0, bk1cropY=H - N, bk2cropX=W - N, bk2cropY=H - N, bgThresh=0)
+        cfg = os.path.join(root, "dataset.json")
+        json.dump(j, open(cfg, "w"))
+        t_gen = time.perf_counter() - t0
+        exe = os.path.join(ROOT, "fpm-opencv_b200", "bin", "fpmMain")
+        env = dict(os.environ, OPENCV_OPENCL_DEVICE="GPU:0", FPM_FOV_OVERLAP="0", FPM_GPUS=",".join(str(i) for i in range(n_gpus)))
+        passes = []
+        for rep in range(2):
+            t1 = time.perf_counter()
+            r = subprocess.run([exe, cfg, str(iters)], capture_output=True, text=True, env=env, timeout=600)
+            wall = time.perf_counter() - t1
+            if r.returncode != 0:
+                return {"error": "fpmMain exited %d: %s" % (r.returncode, (r.stdout + r.stderr)[-400:])}
+            ph = {}
+            for ln in r.stdout.splitlines():
+                if ln.startswith("Full FOV timing:"):
+                    import re
+                    m = re.search(r"setup ([0-9.e+-]+) s, load\+ingest ([0-9.e+-]+) s \((\d+) reader threads\), reconstruction ([0-9.e+-]+) s, gather\+mosaic ([0-9.e+-]+) s", ln)
+                    if m:
+                        ph = {"setup_s": float(m.group(1)), "load_ingest_s": float(m.group(2)), "reader_threads": int(m.group(3)),
+                              "reconstruction_s": float(m.group(4)), "gather_mosaic_s": float(m.group(5))}
+                if ln.startswith("FP Processing Completed"):
+                    ph["fpmMain_total_s"] = float(ln.split("Time:")[1].split("sec")[0])
+            ph["process_wall_s"] = wall
+            passes.append(ph)
+        best = min(passes, key=lambda q: q.get("process_wall_s", 1e30))
+        return {"what": "fpmMain end to end on %d synthetic %dx%d TIFF frames (%.2f GB), %d tiles, %d GPUs" % (
+                    n_leds, W, H, n_leds * W * H * 2 / 1e9, nx * ny, n_gpus),
+                "n_gpus": n_gpus, "wall_s": best["process_wall_s"], "fpmMain_total_s": best.get("fpmMain_total_s"),
+                "phases": best, "passes": passes, "frames_dir": os.path.dirname(root), "generate_s": t_gen,
+                "updates_per_s": nx * ny * n_leds * iters / best["process_wall_s"]}
+    except Exception as e:
+        return {"error": repr(e)}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -165,8 +234,10 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     numa_cpus = bind_to_gpu_cpus(local)        # before the pinned buffers are allocated (first touch = local node)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")       # host-side barrier for the leg in which rank 0 drives all GPUs itself
     peaks_live = measure_peaks(local) if rank == 0 else {}
     g = geometry()
     N, L, n_leds, iters = g["N"], g["L"], g["n_leds"], args.iters
@@ -496,12 +567,20 @@ def run_b200(args):
             line["single_tile"] = single
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(g, distinct[0], iters)
-        print(json.dumps(line), flush=True)
     ctx.close()
     in_buf.close()
     out_buf.close()
+    torch.cuda.synchronize()
+    # ---- full-FOV end to end (BASELINE metric, second half): rank 0 runs the fpmMain executable over all `world` GPUs
+    #      while the other ranks wait on a host-side barrier (their GPUs are idle: every context of this process is closed)
+    if gloo is not None:
+        dist.barrier(group=gloo)
+    if rank == 0:
+        if not args.no_fov_e2e:
+            line["full_fov_e2e"] = fov_e2e_leg(world, g, distinct, iters)
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=gloo)
         dist.destroy_process_group()
 
 
@@ -605,6 +684,7 @@ def main():
     ap.add_argument("--write-combined", type=int, default=0, help="1: write-combined pinned input buffer")
     ap.add_argument("--ref-updates", type=int, default=157)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fov-e2e", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: note: fewer than 3 warm-up steps requested", file=sys.stderr)

@@ -45,10 +45,10 @@ __global__ void __launch_bounds__(1024) ingest_bg_kernel(const uint16_t* frame, 
 // fpm_pruned_fused.cuh (stack_pos_offset), 0: natural order.
 __global__ void __launch_bounds__(256) ingest_tiles_kernel(const uint16_t* frame, int w, const int2* origin, int tile0,
                                                            uint16_t* raw, float* stack, int n_leds, int slot, int Np, int R1,
-                                                           int perm, int divisor, const int* bg) {
+                                                           int perm, int divisor, const int* bg, int bg_imm) {
   const int tile = tile0 + blockIdx.y;
   const int2 o = origin[tile];
-  const int bgv = *bg;
+  const int bgv = bg ? *bg : bg_imm;                      // measured on the device (ingest_bg_kernel) or given by the host
   const size_t base = ((size_t)tile * n_leds + slot) * Np * Np;
   const int R2 = Np / R1;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Np * Np; t += gridDim.x * blockDim.x) {
@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(256) ingest_tiles_kernel(const uint16_t* frame
     stack[base + off] = 1.0f / (float)v;
   }
 }
+
+__global__ void set_bg_kernel(int* bg_out, int v) { *bg_out = v; }          // keeps fpmb200_ingest_bg's table complete
 
 // Feathered mosaic of |objCrop| over a regular tile grid.  Tile (ix, iy) covers low-res pixels
 // [x0 + ix*step, +Np) x [y0 + iy*step, +Np), i.e. f = L/Np times that in the mosaic; where tiles overlap the

@@ -95,9 +95,10 @@ struct fpmb200_ctx {
   uint16_t* frame_dev = nullptr;
   size_t frame_elems = 0;
   int* bg_dev = nullptr;       // [n_leds] background value subtracted from each LED frame
-  int origin_max_x = 0, origin_max_y = 0;
+  int origin_max_x = 0, origin_max_y = 0, origin_min_y = 0;
   float* mosaic_dev = nullptr;
   size_t mosaic_elems = 0;
+  cudaEvent_t events[64] = {};  // stream markers of fpmb200_event_record
   int cluster_req = 0;         // CTAs per tile asked for (0 = choose)
   int cluster = 1;             // CTAs per tile in use (1 = fpm_update_kernel, >1 = fpm_update_cluster_kernel)
   int cpc = 0;                 // bbox columns per CTA of the cluster kernel
@@ -168,6 +169,7 @@ extern "C" void fpmb200_destroy(fpmb200_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_tiles(c);
+  for (cudaEvent_t e : c->events) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -949,10 +951,11 @@ extern "C" int fpmb200_set_tile_origins(fpmb200_ctx* c, const int32_t* x, const 
   CK(copy_sync(c, c->origins, h.data(), sizeof(int2) * n_tiles, cudaMemcpyHostToDevice));
   c->have_origins = true;
   // the largest ROI corner, checked against every frame
-  c->origin_max_x = 0; c->origin_max_y = 0;
+  c->origin_max_x = 0; c->origin_max_y = 0; c->origin_min_y = y[0];
   for (int t = 0; t < n_tiles; ++t) {
     if (x[t] > c->origin_max_x) c->origin_max_x = x[t];
     if (y[t] > c->origin_max_y) c->origin_max_y = y[t];
+    if (y[t] < c->origin_min_y) c->origin_min_y = y[t];
   }
   return FPMB200_OK;
 }
@@ -982,7 +985,42 @@ extern "C" int fpmb200_ingest_frame(fpmb200_ctx* c, int led_slot, const uint16_t
   const int R1 = c->general ? (c->stack_r1 ? c->stack_r1 : 1) : (Np == 64 ? 8 : 16);
   const int bx = (Np * Np + 255) / 256 < 16 ? (Np * Np + 255) / 256 : 16;
   ingest_tiles_kernel<<<dim3(bx, c->n_tiles), 256, 0, st>>>(c->frame_dev, width, c->origins, 0, c->raw, c->stack, c->n_leds,
-                                                             led_slot, Np, R1, c->general ? (c->stack_r1 ? 2 : 0) : 1, divisor, c->bg_dev + led_slot);
+                                                             led_slot, Np, R1, c->general ? (c->stack_r1 ? 2 : 0) : 1, divisor, c->bg_dev + led_slot, 0);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  c->have_stack = true;
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_ingest_rows(fpmb200_ctx* c, int led_slot, const uint16_t* rows, int width, int row0, int n_rows, int divisor,
+                                   int bg_val, void* stream) {
+  if (!c || !rows) return fail(FPMB200_ERR_ARG, "NULL argument");
+  if (!c->have_origins) return fail(FPMB200_ERR_STATE, "fpmb200_set_tile_origins first");
+  if (led_slot < 0 || led_slot >= c->n_leds) return fail(FPMB200_ERR_ARG, "led_slot %d outside [0,%d)", led_slot, c->n_leds);
+  const int Np = c->N;
+  if (width <= 0 || n_rows <= 0 || row0 < 0 || c->origin_max_x + Np > width || c->origin_min_y < row0 ||
+      c->origin_max_y + Np > row0 + n_rows)
+    return fail(FPMB200_ERR_ARG, "rows [%d,%d) x %d columns do not cover this context's tiles (ROI rows %d..%d, columns ..%d)", row0,
+                row0 + n_rows, width, c->origin_min_y, c->origin_max_y + Np, c->origin_max_x + Np);
+  if (divisor < 0) return fail(FPMB200_ERR_ARG, "divisor < 0");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const size_t elems = (size_t)width * n_rows;
+  if (elems > c->frame_elems) {
+    CK(cudaStreamSynchronize(st));
+    cudaFree(c->frame_dev);
+    c->frame_dev = nullptr; c->frame_elems = 0;
+    CK(cudaMalloc(&c->frame_dev, sizeof(uint16_t) * elems));
+    c->frame_elems = elems;
+  }
+  CK(cudaMemcpyAsync(c->frame_dev, rows, sizeof(uint16_t) * elems, cudaMemcpyHostToDevice, st));
+  const int R1 = c->general ? (c->stack_r1 ? c->stack_r1 : 1) : (Np == 64 ? 8 : 16);
+  const int bx = (Np * Np + 255) / 256 < 16 ? (Np * Np + 255) / 256 : 16;
+  // the kernel addresses the frame by absolute row: hand it the (virtual) address of row 0
+  ingest_tiles_kernel<<<dim3(bx, c->n_tiles), 256, 0, st>>>(c->frame_dev - (ptrdiff_t)row0 * width, width, c->origins, 0, c->raw, c->stack,
+                                                             c->n_leds, led_slot, Np, R1, c->general ? (c->stack_r1 ? 2 : 0) : 1, divisor,
+                                                             nullptr, bg_val);
+  set_bg_kernel<<<1, 1, 0, st>>>(c->bg_dev + led_slot, bg_val);
   c->launches += 2;
   CK(cudaGetLastError());
   c->have_stack = true;
@@ -1064,6 +1102,23 @@ extern "C" int fpmb200_host_alloc(unsigned long long bytes, int write_combined, 
 }
 extern "C" int fpmb200_host_free(void* ptr) {
   if (ptr) CK(cudaFreeHost(ptr));
+  return FPMB200_OK;
+}
+
+extern "C" int fpmb200_event_record(fpmb200_ctx* c, int slot, void* stream) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  if (slot < 0 || slot >= 64) return fail(FPMB200_ERR_ARG, "marker slot %d outside 0..63", slot);
+  CK(cudaSetDevice(c->device));
+  if (!c->events[slot]) CK(cudaEventCreateWithFlags(&c->events[slot], cudaEventDisableTiming));
+  CK(cudaEventRecord(c->events[slot], stream ? (cudaStream_t)stream : c->stream));
+  return FPMB200_OK;
+}
+extern "C" int fpmb200_event_sync(fpmb200_ctx* c, int slot) {
+  if (!c) return fail(FPMB200_ERR_ARG, "ctx is NULL");
+  if (slot < 0 || slot >= 64) return fail(FPMB200_ERR_ARG, "marker slot %d outside 0..63", slot);
+  if (!c->events[slot]) return FPMB200_OK;
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(c->events[slot]));
   return FPMB200_OK;
 }
 

@@ -54,7 +54,10 @@ def load():
         "fpmb200_device_buffer": (i, [vp, i, i, C.POINTER(vp), C.POINTER(C.c_ulonglong)]),
         "fpmb200_set_tile_origins": (i, [vp, vp, vp, i]),
         "fpmb200_ingest_frame": (i, [vp, i, vp, i, i, i, i, i, i, i, i, vp]),
+        "fpmb200_ingest_rows": (i, [vp, i, vp, i, i, i, i, i, vp]),
         "fpmb200_ingest_bg": (i, [vp, vp]),
+        "fpmb200_event_record": (i, [vp, i, vp]),
+        "fpmb200_event_sync": (i, [vp, i]),
         "fpmb200_mosaic": (i, [vp, vp, i, i, i, vp, i, vp]),
         "fpmb200_device_alloc": (i, [vp, C.c_ulonglong, C.POINTER(vp)]),
         "fpmb200_device_free": (i, [vp, vp]),
@@ -77,6 +80,7 @@ EXPORTS = ["fpmb200_last_error", "fpmb200_abi_version", "fpmb200_create", "fpmb2
            "fpmb200_upload_pupil_support", "fpmb200_upload_stack", "fpmb200_init_tiles", "fpmb200_run",
            "fpmb200_step", "fpmb200_finalize", "fpmb200_upload_state", "fpmb200_download",
            "fpmb200_download_objcrop", "fpmb200_device_buffer", "fpmb200_set_tile_origins", "fpmb200_ingest_frame",
+           "fpmb200_ingest_rows", "fpmb200_event_record", "fpmb200_event_sync",
            "fpmb200_ingest_bg", "fpmb200_mosaic", "fpmb200_device_alloc", "fpmb200_device_free", "fpmb200_copy_objcrop_to",
            "fpmb200_host_alloc", "fpmb200_host_free", "fpmb200_sync", "fpmb200_kernel_launches", "fpmb200_variant"]
 
@@ -182,6 +186,20 @@ class Context:
                                              int(bk1[0]), int(bk1[1]), int(bk2[0]), int(bk2[1]), int(bg_threshold), stream))
         if stream is None:
             self.sync()          # `f` may be a temporary
+
+    def ingest_rows(self, led_slot, frame, row0, n_rows, divisor, bg_val, stream=None):
+        """rows [row0, row0+n_rows) of `frame` only (a context that owns part of the tile grid), host-computed bg_val"""
+        f = np.ascontiguousarray(frame[row0:row0 + n_rows], dtype=np.uint16)
+        self._ck(self.L.fpmb200_ingest_rows(self._h, int(led_slot), _ptr(f), f.shape[1], int(row0), int(n_rows), int(divisor),
+                                            int(bg_val), stream))
+        if stream is None:
+            self.sync()
+
+    def event_record(self, slot, stream=None):
+        self._ck(self.L.fpmb200_event_record(self._h, int(slot), stream))
+
+    def event_sync(self, slot):
+        self._ck(self.L.fpmb200_event_sync(self._h, int(slot)))
 
     def ingest_bg(self):
         out = np.zeros(self.n_leds, np.int32)

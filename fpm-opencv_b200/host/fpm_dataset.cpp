@@ -231,6 +231,20 @@ void sortLedOrder(FPM_Dataset* d) {                                             
   }
 }
 
+int16_t backgroundValue(const FPM_Dataset& d, const uint16_t* frame, int w) {
+  const int Np = d.Np;
+  auto roiMean = [&](int x0, int y0) {                                                        // cv::mean: sum * (1/N)
+    unsigned long long s = 0;
+    for (int y = 0; y < Np; ++y)
+      for (int x = 0; x < Np; ++x) s += frame[(size_t)(y0 + y) * w + x0 + x];
+    return (double)s * (1.0 / ((double)Np * Np));
+  };
+  const double bk1 = roiMean(d.bk1cropX, d.bk1cropY), bk2 = roiMean(d.bk2cropX, d.bk2cropY);  // :131-134
+  double bg_val = (bk2 + bk1) / 2;                                                            // :136-138
+  if (bg_val > d.bgThreshold) bg_val = d.bgThreshold;
+  return (int16_t)(int)std::round(bg_val);                                                    // :140
+}
+
 bool preprocessFrame(const FPM_Dataset& d, const uint16_t* frame, int w, int h, FPMimg* im, std::string* err) {
   const int Np = d.Np;
   auto inside = [&](int x, int y) { return x >= 0 && y >= 0 && x + Np <= w && y + Np <= h; };
@@ -248,16 +262,7 @@ bool preprocessFrame(const FPM_Dataset& d, const uint16_t* frame, int w, int h, 
       p = (uint16_t)(q < 0 ? 0 : q > 65535 ? 65535 : q);
     }
   }
-  auto roiMean = [&](int x0, int y0) {                                                        // cv::mean: sum * (1/N)
-    unsigned long long s = 0;
-    for (int y = 0; y < Np; ++y)
-      for (int x = 0; x < Np; ++x) s += frame[(size_t)(y0 + y) * w + x0 + x];
-    return (double)s * (1.0 / ((double)Np * Np));
-  };
-  const double bk1 = roiMean(d.bk1cropX, d.bk1cropY), bk2 = roiMean(d.bk2cropX, d.bk2cropY);  // :131-134
-  double bg_val = (bk2 + bk1) / 2;                                                            // :136-138
-  if (bg_val > d.bgThreshold) bg_val = d.bgThreshold;
-  im->bg_val = (int16_t)(int)std::round(bg_val);                                              // :140
+  im->bg_val = backgroundValue(d, frame, w);                                                  // :131-140
   for (auto& p : im->Image) {                                                                 // :143-144 saturating
     int v = (int)p - (int)im->bg_val;
     p = (uint16_t)(v < 0 ? 0 : v > 65535 ? 65535 : v);

@@ -84,6 +84,9 @@ void sortLedOrder(FPM_Dataset* dataset);
 // ROI crop, dark-field exposure divide, two-ROI background estimate and saturating subtraction
 // (fpmMain.cpp:124-144) on a full frame [h][w] (already reduced to one channel).
 bool preprocessFrame(const FPM_Dataset& dataset, const uint16_t* frame, int w, int h, FPMimg* img, std::string* err);
+// FPMimg::bg_val of a frame (fpmMain.cpp:131-140): cv::mean of the two Np x Np background ROIs, averaged, clamped at
+// bgThreshold, rounded.  The ROIs must lie inside the frame (preprocessFrame checks).
+int16_t backgroundValue(const FPM_Dataset& dataset, const uint16_t* frame, int w);
 
 int16_t loadFPMDataset(FPM_Dataset* dataset);   // fpmMain.h:118
 void runFPM(FPM_Dataset* dataset);              // fpmMain.h:119

@@ -6,8 +6,12 @@
 // gathered on the first GPU and blended into one amplitude mosaic.
 #include <dirent.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -25,10 +29,20 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 struct Dev {
   fpmb200_ctx* c = nullptr;
   int first = 0, n = 0;       // tile range [first, first+n) of the grid
+  int row0 = 0, rows = 0;     // frame rows [row0, row0+rows) cover the ROIs of these tiles
   Dev() = default;
   Dev(const Dev&) = delete;
   Dev& operator=(const Dev&) = delete;
   ~Dev() { fpmb200_destroy(c); }            // every exit path (ck() throws) releases the device state
+};
+struct PinnedRing {                          // K page-locked frame buffers (fpmb200_host_alloc)
+  std::vector<void*> p;
+  PinnedRing(int k, size_t bytes) : p(k, nullptr) {
+    for (int i = 0; i < k; ++i) ck(fpmb200_host_alloc(bytes, 0, &p[i]), "fpmb200_host_alloc");
+  }
+  PinnedRing(const PinnedRing&) = delete;
+  ~PinnedRing() { for (void* q : p) fpmb200_host_free(q); }
+  uint16_t* slot(int i) { return (uint16_t*)p[i]; }
 };
 struct DevBuf {                              // device allocation owned by a context
   fpmb200_ctx* c = nullptr;
@@ -95,12 +109,17 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
     cy[k] = im.cropYStart;
   }
 
-  // ---- frame size from the first file; tile grid; contexts ----
-  fpmio::Image16 full;
+  // ---- frame size from the first file's header; tile grid; contexts ----
   std::string err;
-  if (!fpmio::readTiff(d->datasetRoot + files[0].second, full, &err)) throw std::runtime_error(err);
-  const int W = full.width, H = full.height;
+  std::vector<uint8_t> scratch0;
+  int W = 0, H = 0, ch0 = 0;
+  if (!fpmio::readTiffPlane(d->datasetRoot + files[0].second, nullptr, 0, &W, &H, &ch0, scratch0, &err)) throw std::runtime_error(err);
   if (W < Np || H < Np) throw std::runtime_error("frame smaller than one tile");
+  {
+    auto inside = [&](int x, int y) { return x >= 0 && y >= 0 && x + Np <= W && y + Np <= H; };
+    if (!inside(d->bk1cropX, d->bk1cropY) || !inside(d->bk2cropX, d->bk2cropY))
+      throw std::runtime_error("a background ROI leaves the " + std::to_string(W) + "x" + std::to_string(H) + " frame");
+  }
   int nx = 0, ny = 0;
   tileGrid(W, H, Np, overlap, &nx, &ny);
   const int step = Np - overlap, n_tiles = nx * ny;
@@ -114,51 +133,130 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
   }
   makePupilSupport(Np, d->naRadius, &d->pupilSupport);
   std::vector<Dev> devs(G);
-  for (int g = 0; g < G; ++g) {
-    Dev& v = devs[g];
-    v.first = (int)((long long)n_tiles * g / G);
-    v.n = (int)((long long)n_tiles * (g + 1) / G) - v.first;
-    if (v.n == 0) continue;
-    ck(fpmb200_create(devices[g], &v.c), "fpmb200_create");
-    ck(fpmb200_tiles_alloc(v.c, v.n, Np, L, n), "fpmb200_tiles_alloc");
-    ck(fpmb200_set_params(v.c, d->delta1, d->delta2, d->eps, d->literalScalar ? 1 : 0), "fpmb200_set_params");
-    ck(fpmb200_upload_leds(v.c, cx.data(), cy.data(), n), "fpmb200_upload_leds");
-    ck(fpmb200_upload_pupil_support(v.c, d->pupilSupport.data()), "fpmb200_upload_pupil_support");
-    std::vector<int32_t> ox(v.n), oy(v.n);
-    for (int t = 0; t < v.n; ++t) {
-      ox[t] = ((v.first + t) % nx) * step;
-      oy[t] = ((v.first + t) / nx) * step;
-    }
-    ck(fpmb200_set_tile_origins(v.c, ox.data(), oy.data(), v.n), "fpmb200_set_tile_origins");
-    if (d->debug) std::cout << "GPU " << devices[g] << ": tiles [" << v.first << "," << v.first + v.n << ") " << fpmb200_variant(v.c) << std::endl;
+  {
+    // one setup thread per device: CUDA context creation and the allocations of the devices overlap
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g)
+      th.emplace_back([&, g] {
+        try {
+          Dev& v = devs[g];
+          v.first = (int)((long long)n_tiles * g / G);
+          v.n = (int)((long long)n_tiles * (g + 1) / G) - v.first;
+          ck(fpmb200_create(devices[g], &v.c), "fpmb200_create");
+          ck(fpmb200_tiles_alloc(v.c, v.n, Np, L, n), "fpmb200_tiles_alloc");
+          ck(fpmb200_set_params(v.c, d->delta1, d->delta2, d->eps, d->literalScalar ? 1 : 0), "fpmb200_set_params");
+          ck(fpmb200_upload_leds(v.c, cx.data(), cy.data(), n), "fpmb200_upload_leds");
+          ck(fpmb200_upload_pupil_support(v.c, d->pupilSupport.data()), "fpmb200_upload_pupil_support");
+          std::vector<int32_t> ox(v.n), oy(v.n);
+          for (int t = 0; t < v.n; ++t) {
+            ox[t] = ((v.first + t) % nx) * step;
+            oy[t] = ((v.first + t) / nx) * step;
+          }
+          // the frame rows this device's tiles need: only those are sent to it
+          v.row0 = oy[0];
+          v.rows = oy[v.n - 1] + Np - v.row0;
+          ck(fpmb200_set_tile_origins(v.c, ox.data(), oy.data(), v.n), "fpmb200_set_tile_origins");
+        } catch (const std::exception& e) {
+          errs[g] = e.what();
+        }
+      });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; ++g)
+      if (!errs[g].empty()) throw std::runtime_error("GPU " + std::to_string(devices[g]) + ": " + errs[g]);
+    if (d->debug)
+      for (int g = 0; g < G; ++g)
+        std::cout << "GPU " << devices[g] << ": tiles [" << devs[g].first << "," << devs[g].first + devs[g].n << ") rows [" << devs[g].row0
+                  << "," << devs[g].row0 + devs[g].rows << ") " << fpmb200_variant(devs[g].c) << std::endl;
   }
+  const double t_setup = now() - t0;
 
-  // ---- pass 2: every frame is read once and cut into all tiles on the devices (fpmMain.cpp:109-144) ----
+  // ---- pass 2 (fpmMain.cpp:109-144 for every tile at once): a pool of reader threads fills a ring of page-locked
+  //      frame buffers (pread straight into them), the main thread hands every frame, in file order, to the devices --
+  //      each gets only the rows of its tiles, asynchronously -- and a buffer returns to the readers when every device
+  //      has passed the marker recorded behind its copy.  Reading, host-to-device copies and the cut / divide /
+  //      background kernels overlap; every frame is read once, whatever the number of tiles.
   std::cout << "Loading Images..." << std::endl;                                             // :65
-  std::vector<uint16_t> plane;
-  for (size_t f = 0; f < files.size(); ++f) {
-    if (f > 0 && !fpmio::readTiff(d->datasetRoot + files[f].second, full, &err)) throw std::runtime_error(err);
-    if (full.width != W || full.height != H) throw std::runtime_error(files[f].second + ": frame size differs from the first frame");
-    const uint16_t* frame = full.pix.data();
-    if (full.channels != 1) {
-      if (!d->color) throw std::runtime_error(files[f].second + " has several channels but isColor is false");
-      plane.resize((size_t)W * H);
-      for (size_t k = 0; k < plane.size(); ++k) plane[k] = full.pix[k * full.channels];    // channels[2] of BGR (:112-115)
-      frame = plane.data();
+  const double t_load0 = now();
+  const int n_files = (int)files.size();
+  int n_readers = (int)std::thread::hardware_concurrency();
+  if (const char* e = getenv("FPM_READERS")) n_readers = atoi(e);
+  n_readers = std::max(1, std::min(std::min(n_readers, 8), n_files));
+  const int K = std::min(2 * n_readers + 2, 32);                 // ring slots (= marker slots, < 64)
+  const size_t frame_elems = (size_t)W * H;
+  PinnedRing ring(K, frame_elems * sizeof(uint16_t));
+  std::vector<int16_t> frame_bg(n_files, 0);
+  std::vector<std::string> frame_err(n_files);
+  std::vector<char> state(n_files, 0);                           // 0 = not read, 1 = ready, 2 = failed
+  std::mutex mu;
+  std::condition_variable cv;
+  int slots_released = K;                                        // frames [0, slots_released) may be written by the readers
+  std::atomic<int> next_file{0};
+  bool abort_all = false;
+  auto reader = [&]() {
+    std::vector<uint8_t> scratch;
+    for (;;) {
+      const int f = next_file.fetch_add(1);
+      if (f >= n_files) return;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return f < slots_released || abort_all; });
+        if (abort_all) return;
+      }
+      uint16_t* buf = ring.slot(f % K);
+      int w = 0, h = 0, ch = 0;
+      std::string e;
+      bool ok = fpmio::readTiffPlane(d->datasetRoot + files[f].second, buf, frame_elems, &w, &h, &ch, scratch, &e);
+      if (ok && (w != W || h != H)) { ok = false; e = files[f].second + ": frame size differs from the first frame"; }
+      if (ok && ch != 1 && !d->color) { ok = false; e = files[f].second + " has several channels but isColor is false"; }
+      if (ok) frame_bg[f] = backgroundValue(*d, buf, W);                                   // :131-140, once per frame
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        frame_err[f] = e;
+        state[f] = ok ? 1 : 2;
+      }
+      cv.notify_all();
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int r = 0; r < n_readers; ++r) pool.emplace_back(reader);
+  struct Joiner {                                                // every exit path stops and joins the readers
+    std::vector<std::thread>& pool; std::mutex& mu; std::condition_variable& cv; bool& abort_all;
+    ~Joiner() {
+      { std::lock_guard<std::mutex> lk(mu); abort_all = true; }
+      cv.notify_all();
+      for (auto& t : pool) if (t.joinable()) t.join();
+    }
+  } joiner{pool, mu, cv, abort_all};
+  for (int f = 0; f < n_files; ++f) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return state[f] != 0; });
+      if (state[f] == 2) throw std::runtime_error(frame_err[f]);
     }
     const FPMimg& im = d->imageStack.at(files[f].first);
     const int divisor = (d->darkfieldExpMultiplier != 1 && im.illumination_na > d->objectiveNA) ? d->darkfieldExpMultiplier : 1;
-    for (Dev& v : devs)
-      if (v.c) {
-        ck(fpmb200_ingest_frame(v.c, slot_of[files[f].first], frame, W, H, divisor, d->bk1cropX, d->bk1cropY, d->bk2cropX,
-                                d->bk2cropY, (int)d->bgThreshold, nullptr), "fpmb200_ingest_frame");
-      }
-    for (Dev& v : devs)
-      if (v.c) ck(fpmb200_sync(v.c), "fpmb200_sync");                                      // `full` is reused for the next file
+    const uint16_t* frame = ring.slot(f % K);
+    for (Dev& v : devs) {
+      ck(fpmb200_ingest_rows(v.c, slot_of[files[f].first], frame + (size_t)v.row0 * W, W, v.row0, v.rows, divisor, frame_bg[f], nullptr),
+         "fpmb200_ingest_rows");
+      ck(fpmb200_event_record(v.c, f % K, nullptr), "fpmb200_event_record");
+    }
+    // Two frames of device work stay in flight; once every device has passed the marker behind frame g = f - 2, the
+    // frames up to g are consumed (stream order) and the readers may overwrite their slots with frames up to g + K.
+    const int g = f - 2;
+    if (g >= 0) {
+      for (Dev& v : devs) ck(fpmb200_event_sync(v.c, g % K), "fpmb200_event_sync");
+      { std::lock_guard<std::mutex> lk(mu); slots_released = g + K + 1; }
+      cv.notify_all();
+    }
     std::cout << "Loaded: " << files[f].second << ", LED # is: " << files[f].first << std::endl;   // :180-181
   }
+  for (Dev& v : devs) ck(fpmb200_sync(v.c), "fpmb200_sync");
+  const double t_load = now() - t_load0;
 
   // ---- the loop (fpmMain.cpp:345-476) on every tile, all devices concurrently ----
+  const double t_rec0 = now();
   for (Dev& v : devs)
     if (v.c) ck(fpmb200_init_tiles(v.c, 0, v.n, 1, nullptr), "fpmb200_init_tiles");
   for (int16_t itr = 1; itr <= d->itrCount; itr++) {
@@ -173,10 +271,15 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
   for (Dev& v : devs)
     if (v.c) ck(fpmb200_finalize(v.c, 0, v.n, nullptr), "fpmb200_finalize");               // :481
 
+  for (Dev& v : devs) ck(fpmb200_sync(v.c), "fpmb200_sync");
+  const double t_rec = now() - t_rec0;
+
   // ---- final gather on the first GPU + mosaic ----
+  const double t_mos0 = now();
   const int f = L / Np;
   const int Wm = ((nx - 1) * step + Np) * f, Hm = ((ny - 1) * step + Np) * f;
-  std::vector<float> mosaic((size_t)Wm * Hm);
+  PinnedRing mosaic_buf(1, (size_t)Wm * Hm * sizeof(float));
+  float* mosaic = (float*)mosaic_buf.slot(0);
   Dev& root = devs[0];
   DevBuf gbuf;
   void*& gathered = gbuf.p;
@@ -189,12 +292,16 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
     for (Dev& v : devs)
       if (v.c) ck(fpmb200_sync(v.c), "fpmb200_sync");
   }
-  ck(fpmb200_mosaic(root.c, gathered, nx, ny, step, mosaic.data(), 0, nullptr), "fpmb200_mosaic");
+  ck(fpmb200_mosaic(root.c, gathered, nx, ny, step, mosaic, 0, nullptr), "fpmb200_mosaic");
   ck(fpmb200_sync(root.c), "fpmb200_sync");
+  const double t_mos = now() - t_mos0;
   d->secondsTotal = now() - t0;
   std::cout << "FP Processing Completed (Time: " << (float)d->secondsTotal << " sec)" << std::endl;                  // :489
+  std::cout << "Full FOV timing: geometry+device setup " << (float)t_setup << " s, load+ingest " << (float)t_load << " s (" << n_readers << " reader threads), reconstruction "
+            << (float)t_rec << " s, gather+mosaic " << (float)t_mos << " s, " << n_tiles << " tiles x " << n << " LEDs x "
+            << d->itrCount << " iterations = " << (long long)n_tiles * n * d->itrCount << " updates" << std::endl;
   if (!outDir.empty()) {
-    if (!fpmio::writeTiffF32(outDir + "/mosaic_amp.tif", mosaic.data(), Wm, Hm, &err)) std::cout << "ERROR: " << err << std::endl;
+    if (!fpmio::writeTiffF32(outDir + "/mosaic_amp.tif", mosaic, Wm, Hm, &err)) std::cout << "ERROR: " << err << std::endl;
     else std::cout << "Wrote mosaic_amp.tif (" << Wm << "x" << Hm << ") to " << outDir << std::endl;
   }
   return 1;

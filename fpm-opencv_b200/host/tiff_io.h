@@ -17,6 +17,12 @@ struct Image16 {
 };
 
 bool readTiff(const std::string& path, Image16& out, std::string* err);
+// One plane of a frame straight into caller memory (e.g. a page-locked staging buffer): [height][width] uint16, sample
+// 0 of every pixel (grey frames: the pixel; colour frames: the red plane = channels[2] of OpenCV's BGR, the one the
+// reference keeps, fpmMain.cpp:112-115).  Strips are read with pread -- little-endian 16-bit grey frames land in `dst`
+// without an intermediate copy; `scratch` is reused between calls for the other layouts.  dst == nullptr: header only.
+bool readTiffPlane(const std::string& path, uint16_t* dst, size_t dst_elems, int* width, int* height, int* channels,
+                   std::vector<uint8_t>& scratch, std::string* err);
 // single-channel 16-bit uncompressed little-endian TIFF, one strip
 bool writeTiff16(const std::string& path, const uint16_t* pix, int width, int height, std::string* err);
 // single-channel 32-bit float TIFF (SampleFormat = IEEE float), used for amplitude / phase output

@@ -49,3 +49,21 @@ def synth_stack(N: int, L: int, naRadius: int, cropX, cropY, seed: int) -> np.nd
         out[k] = np.abs(np.fft.ifft2(_sh(Fc[ys:ys + N, xs:xs + N]) * S)) ** 2
     out *= 60000.0 / out.max()
     return np.rint(out).astype(np.uint16)
+
+
+def write_tiff16(path, img):
+    """uncompressed single-strip little-endian 16-bit grey TIFF (what the reference's datasets are; libtiff's
+    DumpModeDecode in its profile, output.svg:13,133) -- synthetic frames for the full-FOV legs."""
+    import struct
+    h, w = img.shape
+    data = np.ascontiguousarray(img, dtype="<u2").tobytes()
+    tags = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, 1, 16), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, 8),
+            (277, 3, 1, 1), (278, 4, 1, h), (279, 4, 1, len(data))]
+    ifd = struct.pack("<H", len(tags))
+    for tag, typ, cnt, val in tags:
+        ifd += struct.pack("<HHI", tag, typ, cnt) + (struct.pack("<HH", val, 0) if typ == 3 else struct.pack("<I", val))
+    ifd += struct.pack("<I", 0)
+    with open(path, "wb") as f:
+        f.write(b"II" + struct.pack("<HI", 42, 8 + len(data)))
+        f.write(data)
+        f.write(ifd)

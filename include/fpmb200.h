@@ -115,6 +115,12 @@ int fpmb200_device_buffer(fpmb200_ctx* ctx, int which, int tile, void** ptr, uns
 int fpmb200_set_tile_origins(fpmb200_ctx* ctx, const int32_t* roi_x, const int32_t* roi_y, int n_tiles);
 int fpmb200_ingest_frame(fpmb200_ctx* ctx, int led_slot, const uint16_t* frame, int width, int height, int divisor,
                          int bk1x, int bk1y, int bk2x, int bk2y, int bg_threshold, void* stream);
+/* The same for a context that owns only some of the frame's tiles (several GPUs): `rows` points at frame row `row0`
+ * ([n_rows][width] uint16, pinned for an asynchronous copy) and must cover every ROI of this context's tiles; the
+ * frame's background value (`FPMimg::bg_val`, computed once per frame by the host: fpmhost / backgroundValue) is passed
+ * in, because the two background ROIs need not lie inside these rows. */
+int fpmb200_ingest_rows(fpmb200_ctx* ctx, int led_slot, const uint16_t* rows, int width, int row0, int n_rows, int divisor,
+                        int bg_val, void* stream);
 /* `FPMimg::bg_val` (fpmMain.h:26) of every ingested LED slot, [n_leds]; synchronises. */
 int fpmb200_ingest_bg(fpmb200_ctx* ctx, int32_t* bg_val);
 
@@ -141,6 +147,12 @@ int fpmb200_host_alloc(unsigned long long bytes, int write_combined, void** ptr)
 int fpmb200_host_free(void* ptr);
 
 int fpmb200_sync(fpmb200_ctx* ctx);
+/* Stream markers for callers that pipeline host buffers against the asynchronous calls above without owning a CUDA
+ * runtime: record marker `slot` (0..63) behind everything enqueued so far on `stream` (NULL = the context's stream),
+ * and block the calling thread until the work before the last record of `slot` is done (a never-recorded slot
+ * returns at once). */
+int fpmb200_event_record(fpmb200_ctx* ctx, int slot, void* stream);
+int fpmb200_event_sync(fpmb200_ctx* ctx, int slot);
 
 /* Introspection: kernels launched by this context so far, and the name/shape of the update
  * kernel variant selected for the current allocation (for logs and bench.py). */

@@ -330,6 +330,25 @@ def test_frame_ingest_matches_host_loader(name):
     assert bg[3] == thr and len(set(bg.tolist())) > 2
     for t in (0, n_tiles // 2, n_tiles - 1):
         assert np.array_equal(a.raw_stack(t), ref[t])
+    # a context that owns only tiles 2..4 of the grid and receives only the frame rows they need, with the background
+    # value computed by the host (fpmb200_ingest_rows: the multi-GPU path of run_fov.cpp); markers order the copies
+    sub = list(range(2, 5))
+    r_ctx = c.make_ctx(n_tiles=len(sub))
+    r_ctx.set_tile_origins([xs[t] for t in sub], [ys[t] for t in sub])
+    row0 = min(ys[t] for t in sub)
+    n_rows = max(ys[t] for t in sub) + N - row0
+    for k in range(n_leds):
+        r_ctx.ingest_rows(k, frames[k], row0, n_rows, divisors[k], bg[k])
+        r_ctx.event_record(k % 4)
+    for k in range(4):
+        r_ctx.event_sync(k)
+    r_ctx.sync()
+    assert np.array_equal(r_ctx.ingest_bg(), bg)
+    for i, t in enumerate(sub):
+        assert np.array_equal(r_ctx.raw_stack(i), ref[t])
+    with pytest.raises(Exception):
+        r_ctx.ingest_rows(0, frames[0], row0 + 1, n_rows - 1, 1, 0)        # rows that do not cover the tiles are refused
+    r_ctx.close()
     b_ctx = c.make_ctx(n_tiles=n_tiles)
     for t in range(n_tiles):
         b_ctx.upload_stack(t, ref[t])
