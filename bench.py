@@ -201,8 +201,8 @@ def fov_e2e_leg(n_gpus, g, stacks, iters, W=2560, H=2160):
                     import re
                     m = re.search(r"setup ([0-9.e+-]+) s, load\+ingest ([0-9.e+-]+) s \((\d+) reader threads\), reconstruction ([0-9.e+-]+) s, gather\+mosaic ([0-9.e+-]+) s", ln)
                     if m:
-                        ph = {"setup_s": float(m.group(1)), "load_ingest_s": float(m.group(2)), "reader_threads": int(m.group(3)),
-                              "reconstruction_s": float(m.group(4)), "gather_mosaic_s": float(m.group(5))}
+                        ph.update({"setup_s": float(m.group(1)), "load_ingest_s": float(m.group(2)), "reader_threads": int(m.group(3)),
+                                   "reconstruction_s": float(m.group(4)), "gather_mosaic_s": float(m.group(5))})
                 if ln.startswith("FP Processing Completed"):
                     ph["fpmMain_total_s"] = float(ln.split("Time:")[1].split("sec")[0])
             ph["process_wall_s"] = wall
@@ -320,10 +320,11 @@ def run_b200(args):
 
     def step_e2e(compute=True, d2h=True):
         computed, fetched = state["computed"], state["fetched"]
-        start = torch.cuda.Event()
-        start.record(main)
-        for si in s_ins:
-            si.wait_event(start)
+        if computed[0] is None:                    # first step of a leg: uploads start after whatever main has queued so far
+            start = torch.cuda.Event()
+            start.record(main)
+            for si in s_ins:
+                si.wait_event(start)
         for c in range(n_chunks):
             a = c * chunk
             n = min(chunk, tiles - a)
