@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cstdio>
@@ -133,10 +134,31 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
   }
   makePupilSupport(Np, d->naRadius, &d->pupilSupport);
   std::vector<Dev> devs(G);
+  // staging memory: a ring of page-locked frame buffers for the reader threads and the mosaic's landing buffer --
+  // allocated (cudaHostAlloc is slow: ~0.3 ms per MB) while the devices are being set up
+  const int n_files = (int)files.size();
+  int n_readers = (int)std::thread::hardware_concurrency();
+  if (const char* e = getenv("FPM_READERS")) n_readers = atoi(e);
+  n_readers = std::max(1, std::min(std::min(n_readers, 8), n_files));
+  const int K = std::min(n_readers + 4, 32);                     // ring slots (= marker slots, < 64): readers + frames in flight
+  const size_t frame_elems = (size_t)W * H;
+  const int fz = L / Np;
+  const int Wm = ((nx - 1) * step + Np) * fz, Hm = ((ny - 1) * step + Np) * fz;
+  std::unique_ptr<PinnedRing> ring_p, mosaic_p;
+  double t_pin = 0, t_geom = now() - t0;
   {
     // one setup thread per device: CUDA context creation and the allocations of the devices overlap
     std::vector<std::string> errs(G);
+    std::string pin_err;
     std::vector<std::thread> th;
+    th.emplace_back([&] {
+      try {
+        const double tp = now();
+        ring_p.reset(new PinnedRing(K, frame_elems * sizeof(uint16_t)));
+        mosaic_p.reset(new PinnedRing(1, (size_t)Wm * Hm * sizeof(float)));
+        t_pin = now() - tp;
+      } catch (const std::exception& e) { pin_err = e.what(); }
+    });
     for (int g = 0; g < G; ++g)
       th.emplace_back([&, g] {
         try {
@@ -164,6 +186,7 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
     for (auto& t : th) t.join();
     for (int g = 0; g < G; ++g)
       if (!errs[g].empty()) throw std::runtime_error("GPU " + std::to_string(devices[g]) + ": " + errs[g]);
+    if (!pin_err.empty()) throw std::runtime_error(pin_err);
     if (d->debug)
       for (int g = 0; g < G; ++g)
         std::cout << "GPU " << devices[g] << ": tiles [" << devs[g].first << "," << devs[g].first + devs[g].n << ") rows [" << devs[g].row0
@@ -178,13 +201,7 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
   //      background kernels overlap; every frame is read once, whatever the number of tiles.
   std::cout << "Loading Images..." << std::endl;                                             // :65
   const double t_load0 = now();
-  const int n_files = (int)files.size();
-  int n_readers = (int)std::thread::hardware_concurrency();
-  if (const char* e = getenv("FPM_READERS")) n_readers = atoi(e);
-  n_readers = std::max(1, std::min(std::min(n_readers, 8), n_files));
-  const int K = std::min(2 * n_readers + 2, 32);                 // ring slots (= marker slots, < 64)
-  const size_t frame_elems = (size_t)W * H;
-  PinnedRing ring(K, frame_elems * sizeof(uint16_t));
+  PinnedRing& ring = *ring_p;
   std::vector<int16_t> frame_bg(n_files, 0);
   std::vector<std::string> frame_err(n_files);
   std::vector<char> state(n_files, 0);                           // 0 = not read, 1 = ready, 2 = failed
@@ -276,10 +293,7 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
 
   // ---- final gather on the first GPU + mosaic ----
   const double t_mos0 = now();
-  const int f = L / Np;
-  const int Wm = ((nx - 1) * step + Np) * f, Hm = ((ny - 1) * step + Np) * f;
-  PinnedRing mosaic_buf(1, (size_t)Wm * Hm * sizeof(float));
-  float* mosaic = (float*)mosaic_buf.slot(0);
+  float* mosaic = (float*)mosaic_p->slot(0);
   Dev& root = devs[0];
   DevBuf gbuf;
   void*& gathered = gbuf.p;
@@ -297,6 +311,8 @@ int runFPMFullFOV(FPM_Dataset* d, int overlap, const std::vector<int>& devices, 
   const double t_mos = now() - t_mos0;
   d->secondsTotal = now() - t0;
   std::cout << "FP Processing Completed (Time: " << (float)d->secondsTotal << " sec)" << std::endl;                  // :489
+  std::cout << "Full FOV setup: directory scan + LED geometry " << (float)t_geom << " s, page-locked staging (" << K << " frame buffers + mosaic) "
+            << (float)t_pin << " s in parallel with " << G << " device contexts + allocations" << std::endl;
   std::cout << "Full FOV timing: geometry+device setup " << (float)t_setup << " s, load+ingest " << (float)t_load << " s (" << n_readers << " reader threads), reconstruction "
             << (float)t_rec << " s, gather+mosaic " << (float)t_mos << " s, " << n_tiles << " tiles x " << n << " LEDs x "
             << d->itrCount << " iterations = " << (long long)n_tiles * n * d->itrCount << " updates" << std::endl;
