@@ -318,7 +318,7 @@ def run_b200(args):
     # runs the identical copy schedule without the reconstruction (copy-only leg); `d2h=False` drops the read-back.
     state = {"computed": [None] * n_chunks, "fetched": [None] * n_chunks}
 
-    def step_e2e(compute=True, d2h=True):
+    def step_e2e(compute=True, d2h=True, sub=sub, n_in=n_in):
         computed, fetched = state["computed"], state["fetched"]
         if computed[0] is None:                    # first step of a leg: uploads start after whatever main has queued so far
             start = torch.cuda.Event()
@@ -382,7 +382,12 @@ def run_b200(args):
     # the same copies with no reconstruction in between: what the host link alone allows
     ms_copy = timed_e2e(3, 1, compute=False)
     ms_h2d = timed_e2e(3, 1, compute=False, d2h=False)
-    copy_only = {"ms_per_step": ms_copy, "h2d_only_ms_per_step": ms_h2d,
+    # the same bytes as 16 copies per chunk spread over four streams (no reconstruction competes for the SMs here, so
+    # the conversion kernels do not stall the copies): does splitting the upload help the host link?
+    while len(s_ins) < 4:
+        s_ins.append(torch.cuda.Stream())
+    ms_h2d_split = timed_e2e(3, 1, compute=False, d2h=False, sub=max(1, (chunk + 15) // 16), n_in=4)
+    copy_only = {"ms_per_step": ms_copy, "h2d_only_ms_per_step": ms_h2d, "h2d_only_ms_per_step_4_streams_16_copies_per_chunk": ms_h2d_split,
                  "h2d_gbs_per_gpu": tiles * in_bytes / (ms_h2d * 1e-3) / 1e9,
                  "h2d_gbs_aggregate": world * tiles * in_bytes / (ms_h2d * 1e-3) / 1e9,
                  "both_directions_gbs_aggregate": world * tiles * (in_bytes + out_bytes) / (ms_copy * 1e-3) / 1e9,
