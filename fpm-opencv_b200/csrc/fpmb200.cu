@@ -361,7 +361,8 @@ static int select_variant(fpmb200_ctx* c) {
     factorize(N, fp);
     {
       const char* e = getenv("FPMB200_GENERAL_UNFUSED");
-      c->gfused = fp.nrad <= 8 && general_fused_smem_bytes(N, c->cgr, c->cgc) <= (size_t)c->max_smem_optin && !(e && e[0] == '1');
+      c->gfused = fp.nrad <= 8 && general_fused_smem_bytes(N, c->cgr, c->cgc) <= (size_t)c->max_smem_optin && !(e && e[0] == '1') &&
+                  !c->stack_r1;          // (a position-major stack belongs to fpm_update_pruned_kernel)
     }
     if (c->gfused) {
       c->smem_bytes = general_fused_smem_bytes(N, c->cgr, c->cgc);
@@ -698,6 +699,9 @@ static int run_updates_general_fused(fpmb200_ctx* c, int first, int n, int slot_
 
 // R1 * 100 + R2 of the compiled in-place plan of fpm_update_pruned_kernel for Np, 0 if there is none
 static int pruned_plan(int N) {
+  // (measured: the shipped small tiles through this kernel at two CTAs of 320 threads per SM -- plans 10 x 9 and 10 x 10,
+  //  296 tiles -- give 10.8 M updates/s at Np = 90 against 9.65 M of fpm_update_general_kernel and the same 7.49 M at
+  //  Np = 100; not worth a second stack layout for those sizes)
   switch (N) {
     case 200: return 2010;      // dataset_dogStomach.json as shipped
     case 160: return 1610;
