@@ -317,6 +317,10 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     if (tid == 0)   // pull the next LED's intensity tile towards L2 while this update runs
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(stack + (size_t)nslot * N * N), "r"((unsigned)(N * N * 4)) : "memory");
     float2* wbase = objFc + (size_t)(ys + H) * L + (xs + H);   // absolute address of (iw=0, jw=0)
+    // (Measured on the large-pupil variant -- window in global memory, cfg5: 85 x 85 box, 6.4 M updates/s at 148 tiles:
+    //  prefetch.global.L2 of the next window from here: 6.41 M against 6.47 M without; C2 / E restructured row-wise
+    //  (32 consecutive columns of a row per warp, uniform row addresses, one shared atomic per max-cell, 4 or 8 items in
+    //  flight): 5.85 M.  Neither DRAM latency nor the per-element index arithmetic is what binds C2 there.)
 
     // ===== S1: pending pupil update P += Q / max|objF| (fpmMain.cpp:470-475) for the rows this thread owns, then
     //       Phi = O*P and cols stage A (inverse).  max|P|^2 for this update's object step is reduced on the way. =====
