@@ -5,11 +5,13 @@
 #include <stdint.h>
 #include "fft_regs.cuh"
 #include "fpm_update.cuh"
+#include "fpm_update_narrow.cuh"
 #include "fpm_update_cluster.cuh"
 #include "fpm_general.cuh"
 #include "fpm_general_fused.cuh"
 #include "fpm_pruned_fused.cuh"
 #include "fpm_fov.cuh"
+#include "fpm_fft2d.cuh"
 
 namespace fpm {
 

@@ -60,6 +60,7 @@ struct UpdateParams {
   int ocp;                  // row pitch (float2) of the on-chip window copies: even and >= NC+1 (TMA boxes start on 16 B)
   int cs;                   // log2 rows per max-cell (cells are (1<<cs) rows x 16 columns)
   long long* stage_clk;     // [16] per-stage cycle totals of CTA 0 (only with -DFPM_STAGE_TIMING)
+  int noff[12];             // fpm_update_narrow_kernel: byte offsets of its box-dependent shared-memory arrays (NarrowShape::layout)
 };
 
 template <int N> struct Shape {
@@ -416,7 +417,8 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
       // the wait is free; the load has until C2 (which forwards this update's values into it) to land.
       if (tid == 0 && u > 0) {
         tma_store_wait_all();
-        asm volatile("fence.proxy.async;" ::: "memory");
+        // (a fence.proxy.async without a state space compiles to MEMBAR.ALL.GPU: ~1k cycles on this warp per update)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&wbar, win_bytes);
         tma_load_window(Ocn, &p.tmap, 2 * ((cr_b.x + H + p.xlo) & ~1), cr_b.y + H + p.ylo, tile, &wbar);
       }

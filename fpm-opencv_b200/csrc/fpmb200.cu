@@ -67,6 +67,7 @@ struct fpmb200_ctx {
   // kernel variant
   bool field_smem = false, p_smem = false, q_smem = false;
   bool narrow = false;         // bbox within +-(3*R2-1): the pruned-butterfly instantiation of fpm_update_kernel (N = 128)
+  bool narrow2 = false;        // ... run by fpm_update_narrow_kernel (three phases per update; fpm_update_narrow.cuh)
   int cs = 0;                  // log2 rows per max-cell
   size_t smem_bytes = 0;
   int max_smem_optin = 0, sm_count = 0;
@@ -435,6 +436,7 @@ static int select_variant(fpmb200_ctx* c) {
     const int want = c->cluster_req ? c->cluster_req : (N == 256 ? 8 : (N == 128 && c->n_tiles * 4 <= c->sm_count) ? 4 : 1);
     bool ok = false;
     int max_clusters = 0;
+#ifndef FPM_DEV_FAST
     if (N == 256 && want == 8) ok = cluster_fits<256, 8>(c, &c->cpc, &c->cs, &c->smem_bytes);
     else if (N == 128 && want == 4) {
       ok = cluster_fits<128, 4>(c, &c->cpc, &c->cs, &c->smem_bytes, &max_clusters);
@@ -442,7 +444,9 @@ static int select_variant(fpmb200_ctx* c) {
       if (ok && !c->cluster_req && c->n_tiles > max_clusters) ok = false;
     }
     else if (N == 128 && want == 2) ok = cluster_fits<128, 2>(c, &c->cpc, &c->cs, &c->smem_bytes);
-    else if (want != 1 && c->cluster_req)
+    else
+#endif
+    if (want != 1 && c->cluster_req)
       return fail(FPMB200_ERR_ARG, "%d CTAs per tile is not available for Np=%d (256: 8; 128: 2 or 4; any: 1)", want, N);
     if (ok) {
       c->cluster = want;
@@ -473,6 +477,16 @@ static int select_variant(fpmb200_ctx* c) {
     c->narrow = (N == 128) && c->p_smem && c->q_smem && ylo >= -lim && yhi <= lim && xlo >= -lim && xhi <= lim;
   }
   c->smem_bytes = update_smem_bytes(c, c->field_smem, c->p_smem, c->q_smem, cs);
+  {
+    // narrow pupils on 128 x 128 tiles with one-row max-cells: the three-phase kernel (FPMB200_NARROW_V1=1 keeps the
+    // older one, developer A/B)
+    const char* e = getenv("FPMB200_NARROW_V1");
+    int noff[NarrowShape::NOFF];
+    NarrowShape::layout(yhi - ylo + 1, xhi - xlo + 1, ((xhi - xlo + 1) + 2) & ~1, c->L, noff);
+    const size_t nb = (size_t)noff[NarrowShape::TOTAL];
+    c->narrow2 = c->narrow && c->field_smem && cs == 0 && (c->L % 64) == 0 && !(e && e[0] == '1') && nb <= cap;
+    if (c->narrow2) c->smem_bytes = nb;
+  }
   if (!c->field_smem && !c->field_gmem)
     CK(cudaMalloc(&c->field_gmem, sizeof(float2) * (size_t)N * (N + 1) * c->n_tiles));
   c->ocp = ((xhi - xlo + 1) + 2) & ~1;       // even, with room for the 16-byte alignment of TMA box starts
@@ -496,7 +510,8 @@ static int select_variant(fpmb200_ctx* c) {
     c->have_tmap = true;
   }
   snprintf(c->variant, sizeof c->variant,
-           "fpm_update_kernel<N=%d,field=%s,pupil=%s,dP=%s%s> bbox=[%d..%d]x[%d..%d] maxcell=%dx16 smem=%zuB", N,
+           "%s<N=%d,field=%s,pupil=%s,dP=%s%s> bbox=[%d..%d]x[%d..%d] maxcell=%dx16 smem=%zuB",
+           c->narrow2 ? "fpm_update_narrow_kernel" : "fpm_update_kernel", N,
            c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", c->q_smem ? "smem" : "field",
            c->narrow ? ",pruned radix-16" : "", ylo, yhi, xlo, xhi,
            1 << cs, c->smem_bytes);
@@ -607,11 +622,32 @@ template <int N, int NT, int MINB>
 static int launch_update(fpmb200_ctx* c, const UpdateParams& p, int n_blocks, cudaStream_t st) {
   void (*k)(const UpdateParams) = nullptr;   // (declared __grid_constant__ in the kernel)
   constexpr bool FS = (N <= 128);
-  if constexpr (N == 128) { if (c->p_smem && c->q_smem && c->narrow) k = fpm_update_kernel<N, NT, MINB, FS, true, true, true>; }
+  if constexpr (N == 128) {
+    if (c->narrow2) {
+      // developer A/B: FPMB200_NARROW_NT=1024 runs 32 warps of 64 registers
+      const char* e = getenv("FPMB200_NARROW_NT");
+      const bool big = e && atoi(e) == 1024;
+      UpdateParams pn = p;
+      NarrowShape::layout(c->yhi - c->ylo + 1, c->xhi - c->xlo + 1, c->ocp, c->L, pn.noff);
+      k = big ? fpm_update_narrow_kernel<N, 1024> : fpm_update_narrow_kernel<N, 512>;
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+      k<<<n_blocks, big ? 1024 : 512, c->smem_bytes, st>>>(pn);
+      c->launches++;
+      CK(cudaGetLastError());
+      return FPMB200_OK;
+    }
+#ifndef FPM_DEV_FAST
+    else if (c->p_smem && c->q_smem && c->narrow) k = fpm_update_kernel<N, NT, MINB, FS, true, true, true>;
+#endif
+  }
   if (k) {}
+#ifndef FPM_DEV_FAST
   else if (c->p_smem && c->q_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, true>;
   else if (c->p_smem) k = fpm_update_kernel<N, NT, MINB, FS, true, false>;
   else k = fpm_update_kernel<N, NT, MINB, FS, false, false>;
+#else
+  else return fail(FPMB200_ERR_STATE, "FPM_DEV_FAST build: only the narrow 128 x 128 kernel is compiled");
+#endif
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   k<<<n_blocks, NT, c->smem_bytes, st>>>(p);
   c->launches++;
@@ -680,6 +716,10 @@ static int run_updates_general_fused(fpmb200_ctx* c, int first, int n, int slot_
 #endif
   // two-stage plans with compile-time radices for the sizes of the shipped JSONs (and their neighbours); other sizes
   // take the radices at run time
+#ifdef FPM_DEV_FAST
+  void (*k)(const GeneralFusedParams) = nullptr;
+  return fail(FPMB200_ERR_STATE, "FPM_DEV_FAST build");
+#else
   void (*k)(const GeneralFusedParams) = fpm_update_general_kernel<GEN_NT, 0, 0>;
   switch (general_fused_plan(c->N)) {
     case 1009: k = fpm_update_general_kernel<GEN_NT, 10, 9>; break;
@@ -690,6 +730,7 @@ static int run_updates_general_fused(fpmb200_ctx* c, int first, int n, int slot_
     case 1006: k = fpm_update_general_kernel<GEN_NT, 10, 6>; break;
     default: break;
   }
+#endif
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   k<<<n, GEN_NT, c->smem_bytes, st>>>(p);
   c->launches++;
@@ -726,6 +767,10 @@ static int run_updates_pruned(fpmb200_ctx* c, int first, int n, int slot_begin, 
 #endif
   void (*k)(const PrunedParams) = nullptr;
   const bool nw = c->narrow;      // the box lies within +-3*R2: six-sample butterflies in the stage-A passes (R1 = 20 plans)
+#ifdef FPM_DEV_FAST
+  (void)nw;
+  return fail(FPMB200_ERR_STATE, "FPM_DEV_FAST build");
+#else
   switch (pruned_plan(c->N)) {
     case 2010: k = nw ? fpm_update_pruned_kernel<PRUNED_NT, 20, 10, true> : fpm_update_pruned_kernel<PRUNED_NT, 20, 10, false>; break;
     case 1610: k = fpm_update_pruned_kernel<PRUNED_NT, 16, 10, false>; break;
@@ -734,6 +779,7 @@ static int run_updates_pruned(fpmb200_ctx* c, int first, int n, int slot_begin, 
     case 1608: k = fpm_update_pruned_kernel<PRUNED_NT, 16, 8, false>; break;
     default: return fail(FPMB200_ERR_STATE, "no pruned plan for Np=%d", c->N);
   }
+#endif
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   k<<<n, PRUNED_NT, c->smem_bytes, st>>>(p);
   c->launches++;
@@ -836,15 +882,19 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
   CK(cudaSetDevice(c->device));
   if (c->cluster > 1) {
     p.ocp = c->cpc;
+#ifndef FPM_DEV_FAST
     if (c->N == 256 && c->cluster == 8) return launch_cluster<256, 8>(c, p, n, st);
     if (c->N == 128 && c->cluster == 4) return launch_cluster<128, 4>(c, p, n, st);
     if (c->N == 128 && c->cluster == 2) return launch_cluster<128, 2>(c, p, n, st);
+#endif
     return fail(FPMB200_ERR_STATE, "no cluster kernel for Np=%d x %d CTAs", c->N, c->cluster);
   }
   switch (c->N) {
+#ifndef FPM_DEV_FAST
     case 64: return launch_update<64, 512, 1>(c, p, n, st);
-    case 128: return launch_update<128, 512, 1>(c, p, n, st);
     case 256: return launch_update<256, 512, 1>(c, p, n, st);
+#endif
+    case 128: return launch_update<128, 512, 1>(c, p, n, st);
   }
   return fail(FPMB200_ERR_ARG, "unsupported Np");
 }
@@ -866,12 +916,55 @@ extern "C" int fpmb200_step(fpmb200_ctx* c, int tile, int led_slot) {
   return FPMB200_OK;
 }
 
+// objCrop = IDFT(fftShift(objFc)) for `n` tiles with the planned kernels of fpm_fft2d.cuh; FPMB200_ERR_STATE (without an
+// error message) when Nlarge has no compiled plan
+template <int R0, int R1, int R2>
+static int planned_ifft2d_launch(fpmb200_ctx* c, const float2* src, float2* dst, int n, cudaStream_t st) {
+  using PS = PlanShape<R0, R1, R2>;
+  auto k = plan_fft_kernel<R0, R1, R2, true>;
+  if (PS::smem > (size_t)c->max_smem_optin) return FPMB200_ERR_STATE;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS::smem));
+  PlanFFTParams p;
+  memset(&p, 0, sizeof p);
+  const long long LL = (long long)PS::L * PS::L;
+  p.tw = c->twL; p.src_stride = LL; p.dst_stride = LL;
+  const dim3 grid((PS::L + PS::LINES - 1) / PS::LINES, n);
+  p.src = src; p.dst = dst; p.shift = 1; p.cols = 0; p.scale = 1.f;                         // rows, through the fftShift
+  k<<<grid, 256, PS::smem, st>>>(p);
+  p.src = dst; p.shift = 0; p.cols = 1; p.scale = 1.0f / ((float)PS::L * (float)PS::L);       // columns, in place
+  k<<<grid, 256, PS::smem, st>>>(p);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  return FPMB200_OK;
+}
+static int planned_ifft2d(fpmb200_ctx* c, const float2* src, float2* dst, int n, cudaStream_t st) {
+  switch (c->L) {
+    case 256: return planned_ifft2d_launch<16, 16, 1>(c, src, dst, n, st);
+    case 384: return planned_ifft2d_launch<8, 8, 6>(c, src, dst, n, st);
+    case 512: return planned_ifft2d_launch<8, 8, 8>(c, src, dst, n, st);
+    case 1024: return planned_ifft2d_launch<16, 8, 8>(c, src, dst, n, st);
+    case 1536: return planned_ifft2d_launch<16, 16, 6>(c, src, dst, n, st);
+    case 600: return planned_ifft2d_launch<10, 10, 6>(c, src, dst, n, st);
+    case 360: return planned_ifft2d_launch<10, 6, 6>(c, src, dst, n, st);
+    default: return FPMB200_ERR_STATE;
+  }
+}
+
 extern "C" int fpmb200_finalize(fpmb200_ctx* c, int first, int n, void* stream) {
   int rc = check_range(c, first, n);
   if (rc) return rc;
   CK(cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   const size_t LL = (size_t)c->L * c->L;
+  // Nlarge with a compiled plan: two launches, the fftShift folded into the row pass's loads (fpm_fft2d.cuh);
+  // FPMB200_FINALIZE_GENERIC=1 keeps the run-time-radix path (developer A/B)
+  {
+    const char* e = getenv("FPMB200_FINALIZE_GENERIC");
+    if (!(e && e[0] == '1')) {
+      rc = planned_ifft2d(c, c->objFc + LL * first, c->objCrop + LL * first, n, st);
+      if (rc != FPMB200_ERR_STATE) return rc;
+    }
+  }
   shift_copy_kernel<<<dim3(64, n), 256, 0, st>>>(c->objCrop + LL * first, c->objFc + LL * first, c->L, (long long)LL, (long long)LL);
   c->launches++;
   return fft2d<true>(c, c->objCrop + LL * first, c->L, c->twL, n, (long long)LL, 1.0f / ((float)c->L * (float)c->L), st);
