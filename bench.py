@@ -552,7 +552,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
                          "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram read+write)",
-                         "kernel": "fpm_update_kernel", "kernel_ms_per_launch": kernel_ms,
+                         "kernel": ctx.variant.split("<")[0], "kernel_ms_per_launch": kernel_ms,
                          "flops_per_update": flops_per_update(N), "updates_per_launch": upd_per_launch,
                          "peak_source": onchip_src, "peak_nominal": FP32_PEAK_TFLOPS_NOMINAL},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,

@@ -5,7 +5,7 @@
 #include <stdint.h>
 #include "fft_regs.cuh"
 #include "fpm_update.cuh"
-#include "fpm_update_narrow.cuh"
+#include "fpm_update_phased.cuh"
 #include "fpm_update_cluster.cuh"
 #include "fpm_general.cuh"
 #include "fpm_general_fused.cuh"

@@ -1,36 +1,43 @@
-// fpm_update_narrow.cuh -- the fused sub-aperture update for 128 x 128 tiles with a narrow pupil (sm_100a).
+// fpm_update_phased.cuh -- the fused sub-aperture update, three phases per update (sm_100a).
 //
-// Same algorithm, data layout and results as fpm_update_kernel<128, 512, 1, true, true, true, NARROW> (fpm_update.cuh;
-// loop body fpmMain.cpp:350-475), restructured around what that kernel's stage table showed: half of its cycles went to
-// stages with too little work for 16 warps, separated by eight block-wide barriers.  Here an update is three phases:
+// Same algorithm, data layout and results as fpm_update_kernel<N, 512, 1, true, true, true, .> (fpm_update.cuh; loop body
+// fpmMain.cpp:350-475) for tiles whose field, pupil, pupil increment and windows all live in shared memory with one-row
+// max-cells: N = 128 = 16 x 8 with a narrow pupil (box within +-23: six-sample stage-A butterflies, the shipped 128-pixel
+// configurations and the bench workload) and N = 64 = 8 x 8 (any box).  Restructured around what the older kernel's stage
+// table showed: half of its cycles went to stages with too little work for 16 warps, separated by eight block-wide
+// barriers.  Here an update is three phases:
 //
 //   A   threads < R2*NC:  pending pupil update P += Q / max|objF|, Phi = O*P from the TMA-staged window, inverse
-//                          column stage A (six-sample radix-16 butterflies)
+//                          column stage A
 //       the other warps:   the max-cells of the PREVIOUS update's rectangle are rebuilt from W (off the critical path)
 //   --- block barrier ---
-//   B   per row block (32 rows = 4 warps, named barriers only): inverse column stage B of the block's four k1 (the warp
-//       that owns k1 is a warp of the row block that consumes it), inverse row stages A, B, amplitude replacement,
-//       forward row stages B', A', forward column stage B' of the same four k1.
-//       Before it, every thread scans its share of the grid U of cell maxima EXCLUDING the cells this update's rectangle
-//       touches (U is complete for the previous update since phase A): the maximum of the untouched spectrum.
+//   B   per row block (32 rows, named barriers only): inverse column stage B of the block's k1 (the warps that own a k1
+//       belong to the row block that consumes it), inverse row stages A, B, amplitude replacement, forward row stages
+//       B', A', forward column stage B' of the same k1.
+//       Before it, a thread per spectrum row takes the maximum of the cells this update's rectangle does NOT touch:
+//       one load of the row maximum Rm for most rows, a re-read of the row of U (refreshing Rm) for the rows of this and
+//       of the previous rectangle.
 //   --- block barrier ---
-//   C   one bbox element per lane: the last forward column stage as a direct 16-term DFT of exactly the bbox outputs
-//       (16 of the 128 rows are wanted per column), fused with the object update, the pupil-increment Q, the forward of
-//       the new values into the next LED's window, |O_new|^2 -> W and the running maximum over rectangle + edge pixels.
+//   C   one bbox element per lane: the last forward column stage as a direct R1-term DFT of exactly the bbox outputs,
+//       fused with the object update, the pupil increment Q, the forward of the new values into the next LED's window,
+//       |O_new|^2 -> W and the running maximum over rectangle + edge pixels.
 //   --- block barrier ---   (TMA store of the window; max|objF| = max(untouched cells, rectangle, edges))
 //
 // max|objF| is exact as before (a maximum does not depend on the order it is taken in): the results equal the older
 // kernel's except for the rounding of the last column stage (direct sum instead of a butterfly).
+//
+// Measured on the bench workload (592 tiles of 128 x 128, box 35 x 35, 157 LEDs x 10): 15.0 M updates/s against 14.5 M
+// (update kernel alone).  Also measured, and not adopted: 1024 threads of 64 registers (13.6 M), twiddles of the row
+// stages from constant memory instead of shared memory (14.6 - 14.8 M), the next window requested after S2 or S3
+// instead of S4 (14.9 M).
 #pragma once
 #include "fpm_update.cuh"
 
-// the thread that issues the window's TMA store, waits for it and issues the next load (bulk async-groups are per thread)
+// the thread that issues the window's TMA store, waits for it and issues the next load (bulk async-groups are per
+// thread): a thread of the last warp, which has the least work in phases A and C
 #define FPM_TMA_TID (NT - 1)
 #ifndef FPM_TICK_TID
 #define FPM_TICK_TID 0        // the thread whose stage clocks the timing build reports
-#endif
-#ifndef FPM_TMA_AFTER
-#define FPM_TMA_AFTER 4       // the stage of phase B after which the next window is requested (2, 3 or 4)
 #endif
 
 namespace fpm {
@@ -44,17 +51,19 @@ __device__ __forceinline__ float2 cfma4(float2 acc, float2 a, float4 t) {
   return __ffma2_rn(make_float2(a.y, a.y), make_float2(t.z, t.w), __ffma2_rn(make_float2(a.x, a.x), make_float2(t.x, t.y), acc));
 }
 
-struct NarrowShape {
-  static constexpr int T16P = 9;     // float4 per row of the W16^(r*k) table (8 used; padded against bank conflicts)
-  // Dynamic shared memory of fpm_update_narrow_kernel<128, .>.  No static shared memory exists in the kernel, so the
-  // dynamic segment starts 1024-byte aligned and every offset below is an absolute alignment.  The first part is fixed
-  // at compile time; the offsets that depend on the box reach the kernel through UpdateParams::noff (constant bank:
-  // an address is `base + c[..]`, not a chain of size arithmetic the register allocator has to rematerialise).
+template <int N> struct PhasedShape {
+  static constexpr int R1 = Shape<N>::R1, R2 = Shape<N>::R2;
+  static constexpr bool SIX = (R1 == 16);   // stage-A butterflies see 6 of 16 samples (box within +-(3*R2-1))
+  static constexpr int TK = R1 / 2;         // entries per row of the W_R1^(r*k) table of phase C ...
+  static constexpr int TP = TK + 1;         // ... padded against bank conflicts
+  // Dynamic shared memory.  No static shared memory exists in the kernel, so the dynamic segment starts 1024-byte
+  // aligned and every offset below is an absolute alignment.  The first part is fixed at compile time; the offsets that
+  // depend on the box reach the kernel through UpdateParams::noff (constant bank: an address is `base + c[..]`, not a
+  // chain of size arithmetic the register allocator has to rematerialise).
   enum { WIN0, WIN1, PC, QC, SC, WPIX, UCELL, RMAX, TOTAL, NOFF };
-  static constexpr int N = 128;
   static constexpr size_t off_fld = 0, off_twA = sizeof(float2) * N * (N + 1), off_twB = off_twA + sizeof(float4) * N,
-                          off_red = off_twB + sizeof(float4) * N, off_T16 = off_red + sizeof(float) * 128,
-                          off_var = off_T16 + sizeof(float4) * 16 * T16P;
+                          off_red = off_twB + sizeof(float4) * N, off_T = off_red + sizeof(float) * 128,
+                          off_var = off_T + sizeof(float4) * R1 * TP;
   static_assert(off_var % 128 == 0, "TMA destinations are 128-byte aligned");
   static void layout(int NR, int NC, int ocp, int L, int* off) {
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
@@ -71,18 +80,29 @@ struct NarrowShape {
     off[RMAX] = (int)b; b += sizeof(float) * (size_t)L;
     off[TOTAL] = (int)b;
   }
+  // the boxes this kernel takes (besides: field, P, Q in shared memory, one-row max-cells, Nlarge a multiple of 64)
+  static bool box_ok(int ylo, int yhi, int xlo, int xhi) {
+    const int lim = 3 * R2 - 1;
+    if (SIX) return ylo >= -lim && yhi <= lim && xlo >= -lim && xhi <= lim;
+    return xhi - xlo + 1 <= 64 && yhi - ylo + 1 <= 64;
+  }
 };
 
 template <int N, int NT>
-__global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_constant__ UpdateParams p) {
+__global__ void __launch_bounds__(NT, 1) fpm_update_phased_kernel(const __grid_constant__ UpdateParams p) {
   using S = Shape<N>;
+  using PS = PhasedShape<N>;
   constexpr int R1 = S::R1, R2 = S::R2, PITCH = S::PITCH, CH = S::CH;
   constexpr int H = N / 2, NW = NT / 32, WPB = NT / N;      // WPB warps own a block of 32 rows
-  constexpr int T16P = NarrowShape::T16P;
-  static_assert(N == 128 && R1 == 16 && R2 == 8, "six-sample butterflies: N = 128 = 16 x 8");
+  constexpr bool SIX = PS::SIX;
+  constexpr int NIN = SIX ? 6 : R1;                         // samples a stage-A butterfly reads / a stage-A' butterfly keeps
+  constexpr int TK = PS::TK, TP = PS::TP;
+  static_assert((R1 == 16 || R1 == 8) && R2 == 8, "N = 128 = 16 x 8 or N = 64 = 8 x 8");
   constexpr int WK = NW / R1;                               // warps per k1 in the column B stages
   static_assert(NW % R1 == 0 && WK * (32 / R2) == WPB, "column stage B: the warps of k1 belong to the row block that consumes it");
   static_assert(R2 % WPB == 0 && R1 % WPB == 0, "row work items per warp");
+  // sample k of a stage-A butterfly is input m(k) of the radix-R1 transform, at line index (j0 or i0) + R2*m, wrapped
+  auto m_of = [](int k) constexpr { return SIX ? ((k < 3) ? k : R1 - 6 + k) : k; };
   extern __shared__ __align__(1024) unsigned char smem_raw[];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -92,27 +112,30 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
   const int NR = p.yhi - p.ylo + 1, NC = p.xhi - p.xlo + 1;
   const int gc = L >> 4, gc4 = gc >> 2;                    // max-cells are 1 row x 16 columns (cs == 0); float4 per U row
   const int tq = tid / NC, tr = tid - tq * NC;             // phase A work item (i0, jc)
-  const int nA = R2 * NC;                                  // threads of phase A's butterflies (NC <= 47: < NT)
+  const int nA = R2 * NC;                                  // threads of phase A's butterflies (NC <= 64: <= NT)
+  // the max-cell rebuild of phase A: the threads without a butterfly when there are enough of them, else everybody
+  const bool rb_own = (NT - nA) >= 64;
+  const int rb_tid = rb_own ? tid - nA : tid, rb_n = rb_own ? NT - nA : NT;
 
-  // ---- shared memory carve-up (NarrowShape::layout) ----
-  float2* const fld = reinterpret_cast<float2*>(smem_raw + NarrowShape::off_fld);
-  float4* const twA = reinterpret_cast<float4*>(smem_raw + NarrowShape::off_twA);
-  float4* const twB = reinterpret_cast<float4*>(smem_raw + NarrowShape::off_twB);
-  float* const red = reinterpret_cast<float*>(smem_raw + NarrowShape::off_red);    // per-warp partial maxima of |.|^2:
+  // ---- shared memory carve-up (PS::layout) ----
+  float2* const fld = reinterpret_cast<float2*>(smem_raw + PS::off_fld);
+  float4* const twA = reinterpret_cast<float4*>(smem_raw + PS::off_twA);
+  float4* const twB = reinterpret_cast<float4*>(smem_raw + PS::off_twB);
+  float* const red = reinterpret_cast<float*>(smem_raw + PS::off_red);    // per-warp partial maxima of |.|^2:
   float* const redC = red, *const redU = red + 32, *const redP = red + 64;         //   rectangle + edges, untouched cells, pupil
   float2* const sink2 = reinterpret_cast<float2*>(red + 96);               // where the stores of switched-off lanes go
   float* const sink1 = red + 100;
   uint64_t* const wbar = reinterpret_cast<uint64_t*>(red + 104);           // completion barrier of the window TMA
-  float4* const T16 = reinterpret_cast<float4*>(smem_raw + NarrowShape::off_T16);  // T16[r*T16P + k] = W16^(r*k) as a cfma4 operand
+  float4* const TW = reinterpret_cast<float4*>(smem_raw + PS::off_T);      // TW[r*TP + k] = W_R1^(r*k) as a cfma4 operand
   const int OCP = p.ocp;                                                   // pitch of the window AND of P, Q, S (box-relative)
-  float2* const Ocb0 = reinterpret_cast<float2*>(smem_raw + p.noff[NarrowShape::WIN0]);
-  float2* const Ocb1 = reinterpret_cast<float2*>(smem_raw + p.noff[NarrowShape::WIN1]);
-  float2* const Pc = reinterpret_cast<float2*>(smem_raw + p.noff[NarrowShape::PC]);
-  float2* const Qc = reinterpret_cast<float2*>(smem_raw + p.noff[NarrowShape::QC]);
-  float* const Sc = reinterpret_cast<float*>(smem_raw + p.noff[NarrowShape::SC]);
-  float* const W = reinterpret_cast<float*>(smem_raw + p.noff[NarrowShape::WPIX]);     // |.|^2 of every pixel of the touched cells
-  float* const U = reinterpret_cast<float*>(smem_raw + p.noff[NarrowShape::UCELL]);    // [L][gc] exact cell maxima of |objFc|^2
-  float* const Rm = reinterpret_cast<float*>(smem_raw + p.noff[NarrowShape::RMAX]);    // [L] row maxima of U (see phase B)
+  float2* const Ocb0 = reinterpret_cast<float2*>(smem_raw + p.noff[PS::WIN0]);
+  float2* const Ocb1 = reinterpret_cast<float2*>(smem_raw + p.noff[PS::WIN1]);
+  float2* const Pc = reinterpret_cast<float2*>(smem_raw + p.noff[PS::PC]);
+  float2* const Qc = reinterpret_cast<float2*>(smem_raw + p.noff[PS::QC]);
+  float* const Sc = reinterpret_cast<float*>(smem_raw + p.noff[PS::SC]);
+  float* const W = reinterpret_cast<float*>(smem_raw + p.noff[PS::WPIX]);     // |.|^2 of every pixel of the touched cells
+  float* const U = reinterpret_cast<float*>(smem_raw + p.noff[PS::UCELL]);    // [L][gc] exact cell maxima of |objFc|^2
+  float* const Rm = reinterpret_cast<float*>(smem_raw + p.noff[PS::RMAX]);    // [L] row maxima of U (see phase B)
   const uint32_t win_bytes = (uint32_t)(sizeof(float2) * NR * OCP);
 
   float2* objFc = p.objFc + (size_t)tile * L * L;
@@ -138,6 +161,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
     }
   };
   // phase C work items: one warp per (bbox row, 32 columns), the left-over columns packed 32 elements per warp
+  const int fsh = cb_nfull >> 1;                           // (cb_nfull <= 2: full item `it` is row it >> fsh, segment it & fsh)
   const int nC_full = NR * cb_nfull, nC_items = nC_full + ((NR * cb_nl + 31) >> 5);
   const unsigned nl_mul = (65536u + (unsigned)max(cb_nl, 1) - 1u) / (unsigned)max(cb_nl, 1);   // e / cb_nl = (e * nl_mul) >> 16 (e < 2^11)
 
@@ -150,10 +174,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
     const float2 wb = p.tw[a2 * b2];
     twB[t] = make_float4(wb.x, wb.y, -wb.y, wb.x);
   }
-  for (int t = tid; t < 16 * 8; t += NT) {
-    const int r = t >> 3, k = t & 7;
-    const float2 w = p.tw[((r * k) & 15) * (N / 16)];
-    T16[r * T16P + k] = make_float4(w.x, w.y, -w.y, w.x);
+  for (int t = tid; t < R1 * TK; t += NT) {
+    const int r = t / TK, k = t % TK;
+    const float2 w = p.tw[((r * k) % R1) * (N / R1)];
+    TW[r * TP + k] = make_float4(w.x, w.y, -w.y, w.x);
   }
   for (int t = tid; t < NR * OCP; t += NT) {
     const int ir = t / OCP, jc = t - ir * OCP;
@@ -233,43 +257,48 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
       const int i0 = tq, jc = tr;
       const int j = (p.xlo + jc) & (N - 1);
       const int ob = (i0 - p.ylo) * OCP + jc;
-      float2 Ov[6], Qv[6], Pv[6];
-      int pi[6];
-      bool in[6];
-      static_for<0, 6>([&](auto K) {
+      float2 Ov[NIN], Qv[NIN], Pv[NIN];
+      int pi[NIN];
+      bool in[NIN];
+      static_for<0, NIN>([&](auto K) {
         constexpr int k = decltype(K)::value;
-        constexpr int off = (k < 3) ? R2 * k : R2 * (R1 - 6 + k) - N;      // iw = i0 + off
+        constexpr int m = m_of(k);
+        constexpr int off = (R2 * m < H) ? R2 * m : R2 * m - N;            // iw = i0 + off
         const int iw = i0 + off;
         in[k] = (iw >= p.ylo) && (iw <= p.yhi);
         pi[k] = in[k] ? ob + off * OCP : 0;
         Ov[k] = Oc[pi[k]]; Qv[k] = Qc[pi[k]]; Pv[k] = Pc[pi[k]];
       });
-      float2 w6[6], v[R1];
-      static_for<0, 6>([&](auto K) {
+      float2 w[NIN], v[R1];
+      static_for<0, NIN>([&](auto K) {
         constexpr int k = decltype(K)::value;
         const float2 Pn = cfma(inv_objf_max, Qv[k], Pv[k]);
         if (in[k]) Pc[pi[k]] = Pn;
         pm2 = fmaxf(pm2, in[k] ? fmaf(Pn.x, Pn.x, Pn.y * Pn.y) : 0.f);
         const float2 phi = cmul(Ov[k], Pn);
-        w6[k] = in[k] ? phi : make_float2(0.f, 0.f);
+        w[k] = in[k] ? phi : make_float2(0.f, 0.f);
       });
-      fft16_in6<true>(w6, v);
+      if constexpr (SIX) fft16_in6<true>(w, v);
+      else {
+#pragma unroll
+        for (int k = 0; k < R1; ++k) v[k] = w[k];
+        fftR<R1, true>(v);
+      }
 #pragma unroll
       for (int k1 = 0; k1 < R1; ++k1)
         fld[(i0 + R2 * k1) * PITCH + j] = twmul4(v[k1], twA[k1 * R2 + i0]);
-    } else {
+    }
+    if (rb_tid >= 0 && u > 0) {
       // the cells the previous rectangle touched take their rebuilt maxima (W holds every pixel of those cells)
-      if (u > 0) {
-        const int pwsh = 32 - __clz((pr_ncc << 4) - 1);
-        const unsigned mul = (65536u + (unsigned)pr_ncc - 1u) / (unsigned)pr_ncc;
-        for (int t = tid - nA; t < NR * pr_ncc; t += NT - nA) {
-          const int a = (int)(((unsigned)t * mul) >> 16), b = t - a * pr_ncc;
-          const float4* w4 = reinterpret_cast<const float4*>(W + (a << pwsh) + (b << 4));
-          float m = 0.f;
+      const int pwsh = 32 - __clz((pr_ncc << 4) - 1);
+      const unsigned mul = (65536u + (unsigned)pr_ncc - 1u) / (unsigned)pr_ncc;
+      for (int t = rb_tid; t < NR * pr_ncc; t += rb_n) {
+        const int a = (int)(((unsigned)t * mul) >> 16), b = t - a * pr_ncc;
+        const float4* w4 = reinterpret_cast<const float4*>(W + (a << pwsh) + (b << 4));
+        float m = 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { const float4 v = w4[q]; m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
-          U[(pr_r0 + a) * gc + pr_cc0 + b] = m;
-        }
+        for (int q = 0; q < 4; ++q) { const float4 v = w4[q]; m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
+        U[(pr_r0 + a) * gc + pr_cc0 + b] = m;
       }
     }
     pm2 = warp_max(pm2);                                            // (the warp straddling nA has lanes of both kinds)
@@ -306,10 +335,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
     }
     FPM_TICK(10);
     // window of update u+1 -> the buffer update u-1 released.  Its TMA store was issued at the start of phase A and
-    // must be complete (the windows overlap in the spectrum); the load has the rest of phase B to land.
-    // (fence.proxy.async without a state space compiles to MEMBAR.ALL.GPU, ~1k cycles on the issuing warp's row block.
-    // None is needed: the buffer was last written by the generic proxy before the fence.proxy.async.shared::cta that
-    // precedes the TMA store, and last read by that store.)
+    // must be complete (the windows overlap in the spectrum): requested after S4 the wait is free, and the load has
+    // S5 and S6 to land.  (fence.proxy.async without a state space compiles to MEMBAR.ALL.GPU, ~1k cycles on the issuing
+    // warp's row block.  None is needed: the buffer was last written by the generic proxy before the
+    // fence.proxy.async.shared::cta that precedes the TMA store, and last read by that store.)
     auto next_window = [&]() {
       if (tid == FPM_TMA_TID && u > 0) {
         tma_store_wait_all();
@@ -327,37 +356,40 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
 #pragma unroll
       for (int a = 0; a < R2; ++a) fld[(R2 * k1 + a) * PITCH + js] = v[a];
     });
-    if constexpr (FPM_TMA_AFTER == 2) next_window();
     row_block_sync();
     FPM_TICK(2);
     // ---- S3: inverse row stage A (lanes run over rows; columns outside the bbox are zero, not read) ----
     {
       constexpr int NI = R2 / WPB;
-      auto load6 = [&](int j0, float2 (&w)[6]) {
+      auto load_in = [&](int j0, float2 (&w)[NIN]) {
         const float2* rp = fld + rb_row * PITCH + j0;
-        static_for<0, 6>([&](auto K) {
+        static_for<0, NIN>([&](auto K) {
           constexpr int k = decltype(K)::value;
-          constexpr int m = (k < 3) ? k : R1 - 6 + k;
-          const int jw = (k < 3) ? j0 + R2 * m : j0 + R2 * m - N;
+          constexpr int m = m_of(k);
+          const int jw = (R2 * m < H) ? j0 + R2 * m : j0 + R2 * m - N;
           w[k] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);       // (j0 is warp-uniform)
         });
       };
-      float2 wn[6];
-      load6(rb_sub, wn);
+      float2 wn[NIN];
+      load_in(rb_sub, wn);
       static_for<0, NI>([&](auto Q) {
         constexpr int qi = decltype(Q)::value;
         const int j0 = rb_sub + qi * WPB;
-        float2 w6[6], v[R1];
+        float2 w[NIN], v[R1];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) w6[k] = wn[k];
-        if constexpr (qi + 1 < NI) load6(j0 + WPB, wn);
-        fft16_in6<true>(w6, v);
+        for (int k = 0; k < NIN; ++k) w[k] = wn[k];
+        if constexpr (qi + 1 < NI) load_in(j0 + WPB, wn);
+        if constexpr (SIX) fft16_in6<true>(w, v);
+        else {
+#pragma unroll
+          for (int k = 0; k < R1; ++k) v[k] = w[k];
+          fftR<R1, true>(v);
+        }
         float2* rp = fld + rb_row * PITCH + j0;
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul4(v[k1], twA[k1 * R2 + j0]);
       });
     }
-    if constexpr (FPM_TMA_AFTER == 3) next_window();
     row_block_sync();
     FPM_TICK(3);
     // ---- S4: inverse row stage B + amplitude replacement (fpmMain.cpp:378-393) + forward row stage B' ----
@@ -403,7 +435,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
         for (int q = 0; q < R2; ++q) rp[q] = twmul4(v[q], twB[q * R1 + k1]);
       }
     }
-    if constexpr (FPM_TMA_AFTER == 4) next_window();
+    next_window();
     row_block_sync();
     FPM_TICK(4);
     // ---- S5: forward row stage A' (only bbox columns are stored: nothing else is read afterwards) ----
@@ -427,10 +459,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
           for (int k1 = 0; k1 < R1; ++k1) vn[k1] = rp[WPB + R2 * k1];
         }
         fftR<R1, false>(v);
-        static_for<0, 6>([&](auto K) {
+        static_for<0, NIN>([&](auto K) {                             // (the other outputs are dead code)
           constexpr int k = decltype(K)::value;
-          constexpr int r = (k < 3) ? k : R1 - 6 + k;
-          const int jw = (k < 3) ? q + R2 * r : q + R2 * r - N;
+          constexpr int r = m_of(k);
+          const int jw = (R2 * r < H) ? q + R2 * r : q + R2 * r - N;
           if (jw >= p.xlo && jw <= p.xhi) rp[R2 * r] = v[r];
         });
       });
@@ -459,7 +491,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
       // edge pixels of the touched cells outside the rectangle (unchanged by this update): per rectangle row the left
       // part of the first cell (lanes 0..15) and the right part of the last cell (lanes 16..31).  They read L2
       // (ld.cg): earlier windows were written back by TMA stores.  Issued here, consumed after the element loop.
-      constexpr int EPRE = 3;                                       // rows warp, warp+16, warp+32 (NR <= 47)
+      constexpr int EPRE = (SIX ? 48 : 64) / NW;                    // rows warp, warp + NW, ... (NR <= 47 or 64)
       const int ecw = (lane < 16) ? lane : wcols - 32 + lane;
       const bool evalid = (lane < 16) ? (wc0 + ecw < c0) : (wc0 + ecw > c1);
       float2 eraw[EPRE];
@@ -479,16 +511,16 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
       // one element: (ir, jc) of the bbox; on == false lanes compute on element 0 and store nothing
       auto element = [&](int ir, int jc, bool on) {
         const int iw = p.ylo + ir, i = iw & (N - 1), js = (p.xlo + jc) & (N - 1);
-        const int q = i & (R2 - 1), r = i >> 3;
-        // Phi'(i, j) = sum_k1 fld[R2*k1 + q][j] * W16^(r*k1);  W16^(r*(k+8)) = (-1)^r W16^(r*k)
+        const int q = i & (R2 - 1), r = i / R2;
+        // Phi'(i, j) = sum_k1 fld[R2*k1 + q][j] * W_R1^(r*k1);  W_R1^(r*(k + R1/2)) = (-1)^r W_R1^(r*k)
         const float2* fp = fld + q * PITCH + js;
-        const float4* tp = T16 + r * T16P;
+        const float4* tp = TW + r * TP;
         const float sg = (r & 1) ? -1.f : 1.f;
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          const float2 y0 = cfma(sg, fp[(R2 * (k + 8)) * PITCH], fp[(R2 * k) * PITCH]);
-          const float2 y1 = cfma(sg, fp[(R2 * (k + 9)) * PITCH], fp[(R2 * (k + 1)) * PITCH]);
+        for (int k = 0; k < TK; k += 2) {
+          const float2 y0 = cfma(sg, fp[(R2 * (k + TK)) * PITCH], fp[(R2 * k) * PITCH]);
+          const float2 y1 = cfma(sg, fp[(R2 * (k + TK + 1)) * PITCH], fp[(R2 * (k + 1)) * PITCH]);
           acc0 = cfma4(acc0, y0, tp[k]);
           acc1 = cfma4(acc1, y1, tp[k + 1]);
         }
@@ -521,12 +553,12 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_narrow_kernel(const __grid_c
         *(on ? Qc + t : sink2) = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
       };
       auto decode = [&](int it, int& ir, int& jc) -> bool {            // (branch-free: the two elements of a pair interleave)
-        const bool full = it < nC_full;                                // (cb_nfull <= 1: NC <= 47)
+        const bool full = it < nC_full;
         const int e = ((it - nC_full) << 5) + lane;
         const bool on = full || ((it < nC_items) && (e < NR * cb_nl));
         const int er = (int)(((unsigned)e * nl_mul) >> 16);
-        ir = full ? it : (on ? er : 0);
-        jc = full ? lane : (on ? (cb_nfull << 5) + e - er * cb_nl : 0);
+        ir = full ? (it >> fsh) : (on ? er : 0);
+        jc = full ? ((it & fsh) << 5) + lane : (on ? (cb_nfull << 5) + e - er * cb_nl : 0);
         return on;
       };
       for (int it = warp; it < nC_items; it += 2 * NW) {

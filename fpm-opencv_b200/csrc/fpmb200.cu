@@ -67,7 +67,7 @@ struct fpmb200_ctx {
   // kernel variant
   bool field_smem = false, p_smem = false, q_smem = false;
   bool narrow = false;         // bbox within +-(3*R2-1): the pruned-butterfly instantiation of fpm_update_kernel (N = 128)
-  bool narrow2 = false;        // ... run by fpm_update_narrow_kernel (three phases per update; fpm_update_narrow.cuh)
+  bool phased = false;         // run by fpm_update_phased_kernel (three phases per update; fpm_update_phased.cuh)
   int cs = 0;                  // log2 rows per max-cell
   size_t smem_bytes = 0;
   int max_smem_optin = 0, sm_count = 0;
@@ -478,14 +478,17 @@ static int select_variant(fpmb200_ctx* c) {
   }
   c->smem_bytes = update_smem_bytes(c, c->field_smem, c->p_smem, c->q_smem, cs);
   {
-    // narrow pupils on 128 x 128 tiles with one-row max-cells: the three-phase kernel (FPMB200_NARROW_V1=1 keeps the
-    // older one, developer A/B)
-    const char* e = getenv("FPMB200_NARROW_V1");
-    int noff[NarrowShape::NOFF];
-    NarrowShape::layout(yhi - ylo + 1, xhi - xlo + 1, ((xhi - xlo + 1) + 2) & ~1, c->L, noff);
-    const size_t nb = (size_t)noff[NarrowShape::TOTAL];
-    c->narrow2 = c->narrow && c->field_smem && cs == 0 && (c->L % 64) == 0 && !(e && e[0] == '1') && nb <= cap;
-    if (c->narrow2) c->smem_bytes = nb;
+    // everything on chip with one-row max-cells, 64 x 64 tiles or narrow pupils on 128 x 128 tiles: the three-phase
+    // kernel (FPMB200_UPDATE_V1=1 keeps fpm_update_kernel, developer A/B and the tests of that kernel)
+    const char* e = getenv("FPMB200_UPDATE_V1");
+    const int NRb = yhi - ylo + 1, NCb = xhi - xlo + 1, ocp = (NCb + 2) & ~1;
+    int noff[PhasedShape<128>::NOFF];
+    bool ok = c->field_smem && c->p_smem && c->q_smem && cs == 0 && (c->L % 64) == 0 && !(e && e[0] == '1');
+    if (ok && N == 128) { ok = c->narrow && PhasedShape<128>::box_ok(ylo, yhi, xlo, xhi); PhasedShape<128>::layout(NRb, NCb, ocp, c->L, noff); }
+    else if (ok && N == 64) { ok = PhasedShape<64>::box_ok(ylo, yhi, xlo, xhi); PhasedShape<64>::layout(NRb, NCb, ocp, c->L, noff); }
+    else ok = false;
+    c->phased = ok && (size_t)noff[PhasedShape<128>::TOTAL] <= cap;
+    if (c->phased) c->smem_bytes = (size_t)noff[PhasedShape<128>::TOTAL];
   }
   if (!c->field_smem && !c->field_gmem)
     CK(cudaMalloc(&c->field_gmem, sizeof(float2) * (size_t)N * (N + 1) * c->n_tiles));
@@ -511,7 +514,7 @@ static int select_variant(fpmb200_ctx* c) {
   }
   snprintf(c->variant, sizeof c->variant,
            "%s<N=%d,field=%s,pupil=%s,dP=%s%s> bbox=[%d..%d]x[%d..%d] maxcell=%dx16 smem=%zuB",
-           c->narrow2 ? "fpm_update_narrow_kernel" : "fpm_update_kernel", N,
+           c->phased ? "fpm_update_phased_kernel" : "fpm_update_kernel", N,
            c->field_smem ? "smem" : "gmem", c->p_smem ? "smem" : "gmem", c->q_smem ? "smem" : "field",
            c->narrow ? ",pruned radix-16" : "", ylo, yhi, xlo, xhi,
            1 << cs, c->smem_bytes);
@@ -622,20 +625,20 @@ template <int N, int NT, int MINB>
 static int launch_update(fpmb200_ctx* c, const UpdateParams& p, int n_blocks, cudaStream_t st) {
   void (*k)(const UpdateParams) = nullptr;   // (declared __grid_constant__ in the kernel)
   constexpr bool FS = (N <= 128);
-  if constexpr (N == 128) {
-    if (c->narrow2) {
-      // developer A/B: FPMB200_NARROW_NT=1024 runs 32 warps of 64 registers
-      const char* e = getenv("FPMB200_NARROW_NT");
-      const bool big = e && atoi(e) == 1024;
+  if constexpr (N == 128 || N == 64) {
+    if (c->phased) {
       UpdateParams pn = p;
-      NarrowShape::layout(c->yhi - c->ylo + 1, c->xhi - c->xlo + 1, c->ocp, c->L, pn.noff);
-      k = big ? fpm_update_narrow_kernel<N, 1024> : fpm_update_narrow_kernel<N, 512>;
+      PhasedShape<N>::layout(c->yhi - c->ylo + 1, c->xhi - c->xlo + 1, c->ocp, c->L, pn.noff);
+      k = fpm_update_phased_kernel<N, 512>;
       CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-      k<<<n_blocks, big ? 1024 : 512, c->smem_bytes, st>>>(pn);
+      k<<<n_blocks, 512, c->smem_bytes, st>>>(pn);
       c->launches++;
       CK(cudaGetLastError());
       return FPMB200_OK;
     }
+  }
+  if constexpr (N == 128) {
+    if (false) {}
 #ifndef FPM_DEV_FAST
     else if (c->p_smem && c->q_smem && c->narrow) k = fpm_update_kernel<N, NT, MINB, FS, true, true, true>;
 #endif
@@ -891,9 +894,9 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
   }
   switch (c->N) {
 #ifndef FPM_DEV_FAST
-    case 64: return launch_update<64, 512, 1>(c, p, n, st);
     case 256: return launch_update<256, 512, 1>(c, p, n, st);
 #endif
+    case 64: return launch_update<64, 512, 1>(c, p, n, st);
     case 128: return launch_update<128, 512, 1>(c, p, n, st);
   }
   return fail(FPMB200_ERR_ARG, "unsupported Np");

@@ -121,6 +121,41 @@ def test_full_run_parity(name, iters, ctas):
     ctx.close()
 
 
+@pytest.mark.parametrize("name,n_steps,iters", [("cfg1_mono_np64", 30, 3), ("cfg4_dogStomach_np128", 30, 2)])
+def test_older_update_kernel_parity(name, n_steps, iters, monkeypatch):
+    """The three-phase kernel (fpm_update_phased_kernel) is the library's choice for 64 x 64 tiles and for narrow pupils
+    on 128 x 128 tiles; FPMB200_UPDATE_V1=1 keeps fpm_update_kernel, which still serves every other geometry (coarser
+    max-cells, Nlarge not a multiple of 64).  Both are held to the same per-step and full-run tolerances, and agree
+    with each other to rounding (the last column stage is a direct sum in one and a butterfly in the other)."""
+    c = T.case(name)
+    new = c.make_ctx(cluster=1)
+    assert "fpm_update_phased_kernel" in new.variant, new.variant
+    monkeypatch.setenv("FPMB200_UPDATE_V1", "1")
+    old = c.make_ctx(cluster=1)
+    assert "fpm_update_kernel<" in old.variant, old.variant
+    st = orc.init_state(c.stack, c.L, c.r)
+    worst = 0.0
+    for k in range(n_steps):
+        for ctx in (old, new):
+            ctx.upload_state(0, T.corner(st.objFc), st.P)
+        orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+        for ctx in (old, new):
+            ctx.step(0, k)
+            worst = max(worst, *compare(ctx, st, tol=STEP_TOL, crop=False))
+    for ctx in (old, new):
+        ctx.init_tiles()
+        ctx.run(iters)
+        ctx.finalize()
+    ref = c.oracle_run(iters)
+    e_old, e_new = compare(old, ref), compare(new, ref)
+    for x, y in zip(old.download(0), new.download(0)):
+        assert orc.rel_l2(x, y) < 1e-5
+    note("older vs three-phase kernel %s: per-step worst %.2e; %d iterations: objF %.2e / %.2e, pupil %.2e / %.2e" % (
+        name, worst, iters, e_old[0], e_new[0], e_old[1], e_new[1]))
+    old.close()
+    new.close()
+
+
 def test_full_run_parity_kappa0():
     c = T.case("cfg1_mono_np64")
     ctx = c.make_ctx(kappa=0)

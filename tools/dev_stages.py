@@ -41,6 +41,18 @@ for name in names:
             print("   total %.0f cycles/update" % v[1:16].sum())
             ctx.close()
             continue
+        if "fpm_update_phased_kernel" in ctx.variant:
+            # ticks of fpm_update_phased_kernel; a tick right after a block barrier records its issue, the wait lands in the
+            # next tick
+            print(name, "tiles", n_tiles, ctx.variant)
+            for k, lab in ((9, "top: max|objF| (+ wait of the C barrier)"), (1, "A  P+=Q, O*P, inv col A | cell rebuild"), (10, "B  untouched-cell maximum (+ A barrier)"),
+                           (2, "S2 inv col B"), (3, "S3 inv row A"), (4, "S4 inv row B + amplitude + fwd row B'"), (5, "S5 fwd row A'"),
+                           (6, "S6 fwd col B'"), (11, "-"), (12, "C  window wait (+ B barrier)"), (13, "C  edge loads, max|P|"),
+                           (15, "C  fwd col A' (direct) + object update"), (14, "C  edges -> W, warp max"), (8, "C  fence, barrier issue")):
+                print("   %-44s %8.0f cyc  %5.1f%%" % (lab, v[k], 100 * v[k] / v[1:16].sum()))
+            print("   total %.0f cycles/update (thread %s of CTA 0)" % (v[1:16].sum(), os.environ.get("FPM_TICK_TID", "0")))
+            ctx.close()
+            continue
         print(name, "tiles", n_tiles, ctx.variant)
         for k in range(1, 11):
             print("   %-20s %8.0f cyc  %5.1f%%" % (labels[k], v[k], 100 * v[k] / v[1:16].sum()))
