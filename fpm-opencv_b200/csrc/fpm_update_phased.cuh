@@ -29,7 +29,8 @@
 // Measured on the bench workload (592 tiles of 128 x 128, box 35 x 35, 157 LEDs x 10): 15.0 M updates/s against 14.5 M
 // (update kernel alone).  Also measured, and not adopted: 1024 threads of 64 registers (13.6 M), twiddles of the row
 // stages from constant memory instead of shared memory (14.6 - 14.8 M), the next window requested after S2 or S3
-// instead of S4 (14.9 M).
+// instead of S4 (14.9 M), the two elements a thread processes back to back in phase C explicitly interleaved (all loads
+// and arithmetic of both before the stores of either: 14.94 M against 14.98 M -- phase C is issue-bound, not latency-bound).
 #pragma once
 #include "fpm_update.cuh"
 

@@ -199,7 +199,12 @@ static int tiles_alloc_impl(fpmb200_ctx* c, int n_tiles, int Np, int Nlarge, int
   CK(cudaMalloc(&c->crop, sizeof(short2) * n_leds));
   CK(cudaMalloc(&c->twN, sizeof(float2) * Np));
   CK(cudaMalloc(&c->twL, sizeof(float2) * Nlarge));
-  c->scratch_elems = LL > NN * 64 ? LL : NN * 64;
+  {
+    // staging for the spectrum seeds of as many tiles per batch as 256 MB hold (at least 64), and one spectrum
+    size_t nb = std::min<size_t>((size_t)n_tiles, ((size_t)256 << 20) / (sizeof(float2) * NN));
+    nb = std::max<size_t>(nb, 64);
+    c->scratch_elems = std::max(LL, NN * nb);
+  }
   CK(cudaMalloc(&c->scratch, sizeof(float2) * c->scratch_elems));
   CK(cudaMemsetAsync(c->objFc, 0, sizeof(float2) * LL * n_tiles, c->stream));
   CK(cudaMemsetAsync(c->objCrop, 0, sizeof(float2) * LL * n_tiles, c->stream));
@@ -368,6 +373,8 @@ static int select_variant(fpmb200_ctx* c) {
     if (c->gfused) {
       c->smem_bytes = general_fused_smem_bytes(N, c->cgr, c->cgc);
       const int plan = general_fused_plan(N);
+      // (measured: the pupil kept in shared memory, compact over the box, changes nothing -- 9.63 against 9.53 M updates/s
+      //  at Np = 90, 7.41 against 7.43 M at Np = 100: the batched L2 loads of P were already hidden)
       char radices[64];
       if (plan) snprintf(radices, sizeof radices, "radix %d x %d in registers, pruned to the pupil box", plan / 100, plan % 100);
       else snprintf(radices, sizeof radices, "run-time radices, %d stages", fp.nrad);
@@ -595,6 +602,52 @@ static int fft2d(fpmb200_ctx* c, float2* data, int n, const float2* tw, int batc
   return FPMB200_OK;
 }
 
+// n images of L x L through the planned kernels of fpm_fft2d.cuh (rows src -> dst, optionally through the fftShift;
+// columns in place); FPMB200_ERR_STATE (without an error message) when L has no compiled plan
+template <int R0, int R1, int R2, bool INV>
+static int planned_fft2d_launch(fpmb200_ctx* c, const float2* src, float2* dst, const float2* tw, int n, int shift, float scale,
+                                cudaStream_t st) {
+  using PS = PlanShape<R0, R1, R2>;
+  auto k = plan_fft_kernel<R0, R1, R2, INV>;
+  if (PS::smem > (size_t)c->max_smem_optin) return FPMB200_ERR_STATE;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS::smem));
+  PlanFFTParams p;
+  memset(&p, 0, sizeof p);
+  const long long LL = (long long)PS::L * PS::L;
+  p.tw = tw; p.src_stride = LL; p.dst_stride = LL;
+  const dim3 grid((PS::L + PS::LINES - 1) / PS::LINES, n);
+  p.src = src; p.dst = dst; p.shift = shift; p.cols = 0; p.scale = 1.f;       // rows
+  k<<<grid, 256, PS::smem, st>>>(p);
+  p.src = dst; p.shift = 0; p.cols = 1; p.scale = scale;                      // columns, in place
+  k<<<grid, 256, PS::smem, st>>>(p);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  return FPMB200_OK;
+}
+// objCrop = IDFT(fftShift(objFc)), fpmMain.cpp:481
+static int planned_ifft2d(fpmb200_ctx* c, const float2* src, float2* dst, int n, cudaStream_t st) {
+  const float sc = 1.0f / ((float)c->L * (float)c->L);
+  switch (c->L) {
+    case 256: return planned_fft2d_launch<16, 16, 1, true>(c, src, dst, c->twL, n, 1, sc, st);
+    case 384: return planned_fft2d_launch<8, 8, 6, true>(c, src, dst, c->twL, n, 1, sc, st);
+    case 512: return planned_fft2d_launch<8, 8, 8, true>(c, src, dst, c->twL, n, 1, sc, st);
+    case 1024: return planned_fft2d_launch<16, 8, 8, true>(c, src, dst, c->twL, n, 1, sc, st);
+    case 1536: return planned_fft2d_launch<16, 16, 6, true>(c, src, dst, c->twL, n, 1, sc, st);
+    case 600: return planned_fft2d_launch<10, 10, 6, true>(c, src, dst, c->twL, n, 1, sc, st);
+    case 360: return planned_fft2d_launch<10, 6, 6, true>(c, src, dst, c->twL, n, 1, sc, st);
+    default: return FPMB200_ERR_STATE;
+  }
+}
+// forward Np x Np transform of the spectrum seed, in place (fpmMain.cpp:325)
+static int planned_seed_fft2d(fpmb200_ctx* c, float2* data, int n, cudaStream_t st) {
+  switch (c->N) {
+    case 64: return planned_fft2d_launch<8, 8, 1, false>(c, data, data, c->twN, n, 0, 1.f, st);
+    case 128: return planned_fft2d_launch<16, 8, 1, false>(c, data, data, c->twN, n, 0, 1.f, st);
+    case 256: return planned_fft2d_launch<16, 16, 1, false>(c, data, data, c->twN, n, 0, 1.f, st);
+    default: return FPMB200_ERR_STATE;
+  }
+}
+
 extern "C" int fpmb200_init_tiles(fpmb200_ctx* c, int first, int n, int init_slot, void* stream) {
   int rc = check_range(c, first, n);
   if (rc) return rc;
@@ -613,7 +666,12 @@ extern "C" int fpmb200_init_tiles(fpmb200_ctx* c, int first, int n, int init_slo
       case 256: init_amp_kernel<256><<<dim3(16, b), 256, 0, st>>>(c->scratch, c->stack, c->n_leds, init_slot, t0); break;
     }
     c->launches++;
-    if ((rc = fft2d<false>(c, c->scratch, N, c->twN, b, (long long)N * N, 1.f, st))) return rc;
+    {
+      const char* e = getenv("FPMB200_FINALIZE_GENERIC");
+      rc = (e && e[0] == '1') ? FPMB200_ERR_STATE : planned_seed_fft2d(c, c->scratch, b, st);
+      if (rc == FPMB200_ERR_STATE) rc = fft2d<false>(c, c->scratch, N, c->twN, b, (long long)N * N, 1.f, st);
+      if (rc) return rc;
+    }
     init_place_kernel<<<dim3(64, b), 256, 0, st>>>(c->objFc, c->pupil, c->scratch, c->support, N, L, t0);
     c->launches++;
   }
@@ -917,40 +975,6 @@ extern "C" int fpmb200_step(fpmb200_ctx* c, int tile, int led_slot) {
   if ((rc = run_updates(c, tile, 1, led_slot, 1, c->stream))) return rc;
   CK(cudaStreamSynchronize(c->stream));
   return FPMB200_OK;
-}
-
-// objCrop = IDFT(fftShift(objFc)) for `n` tiles with the planned kernels of fpm_fft2d.cuh; FPMB200_ERR_STATE (without an
-// error message) when Nlarge has no compiled plan
-template <int R0, int R1, int R2>
-static int planned_ifft2d_launch(fpmb200_ctx* c, const float2* src, float2* dst, int n, cudaStream_t st) {
-  using PS = PlanShape<R0, R1, R2>;
-  auto k = plan_fft_kernel<R0, R1, R2, true>;
-  if (PS::smem > (size_t)c->max_smem_optin) return FPMB200_ERR_STATE;
-  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS::smem));
-  PlanFFTParams p;
-  memset(&p, 0, sizeof p);
-  const long long LL = (long long)PS::L * PS::L;
-  p.tw = c->twL; p.src_stride = LL; p.dst_stride = LL;
-  const dim3 grid((PS::L + PS::LINES - 1) / PS::LINES, n);
-  p.src = src; p.dst = dst; p.shift = 1; p.cols = 0; p.scale = 1.f;                         // rows, through the fftShift
-  k<<<grid, 256, PS::smem, st>>>(p);
-  p.src = dst; p.shift = 0; p.cols = 1; p.scale = 1.0f / ((float)PS::L * (float)PS::L);       // columns, in place
-  k<<<grid, 256, PS::smem, st>>>(p);
-  c->launches += 2;
-  CK(cudaGetLastError());
-  return FPMB200_OK;
-}
-static int planned_ifft2d(fpmb200_ctx* c, const float2* src, float2* dst, int n, cudaStream_t st) {
-  switch (c->L) {
-    case 256: return planned_ifft2d_launch<16, 16, 1>(c, src, dst, n, st);
-    case 384: return planned_ifft2d_launch<8, 8, 6>(c, src, dst, n, st);
-    case 512: return planned_ifft2d_launch<8, 8, 8>(c, src, dst, n, st);
-    case 1024: return planned_ifft2d_launch<16, 8, 8>(c, src, dst, n, st);
-    case 1536: return planned_ifft2d_launch<16, 16, 6>(c, src, dst, n, st);
-    case 600: return planned_ifft2d_launch<10, 10, 6>(c, src, dst, n, st);
-    case 360: return planned_ifft2d_launch<10, 6, 6>(c, src, dst, n, st);
-    default: return FPMB200_ERR_STATE;
-  }
 }
 
 extern "C" int fpmb200_finalize(fpmb200_ctx* c, int first, int n, void* stream) {
