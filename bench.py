@@ -329,7 +329,10 @@ def run_b200(args):
             a = c * chunk
             n = min(chunk, tiles - a)
             for k, b in enumerate(range(a, a + n, sub)):
-                si = s_ins[k % n_in]
+                # consecutive upload calls alternate between the copy streams: every upload ends with the 1/I conversion
+                # kernel, which cannot start before the persistent update kernel of the chunk in flight leaves the SMs --
+                # on a single stream the NEXT chunk's copy would wait behind it
+                si = s_ins[(c * ((n + sub - 1) // sub) + k) % n_in]
                 if computed[c] is not None:
                     si.wait_event(computed[c])
                 ctx.upload_stack_ptr(b, min(sub, a + n - b), in_buf.ptr + b * in_bytes, si.cuda_stream)
@@ -685,7 +688,7 @@ def main():
     # one upload call per chunk on one stream: measured on one B200, 13 calls of 12 tiles on two streams HALVED e2e
     # (7.96 M vs 13.2 M updates/s): every call ends with the uint16 -> 1/I conversion kernel, which needs an SM and
     # waits for a CTA of the persistent update kernel to retire (16.8 ms) -- the copies queued behind it stall
-    ap.add_argument("--h2d-streams", type=int, default=1, help="copy streams the uploads of one chunk are spread over")
+    ap.add_argument("--h2d-streams", type=int, default=2, help="copy streams the uploads of one chunk are spread over")
     ap.add_argument("--h2d-tiles", type=int, default=148, help="tiles per upload call (12 tiles = 62 MB)")
     ap.add_argument("--write-combined", type=int, default=0, help="1: write-combined pinned input buffer")
     ap.add_argument("--ref-updates", type=int, default=157)

@@ -95,12 +95,12 @@ __global__ void __launch_bounds__(256) gen_object_update(const GeneralParams p) 
     const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
     const float2 num = cmulc(d, Pv);
     const float A = pa2 + p.delta2;
-    const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
+    const float sc = sqrt_fast(pa2) * inv_pmax * rcp_fast(fmaf(A, A, kd2 * kd2));
     *op = make_float2(Ov.x + (num.x * A + num.y * kd2) * sc, Ov.y + (num.y * A - num.x * kd2) * sc);
     const float oa2 = fmaf(Ov.x, Ov.x, Ov.y * Ov.y);
     const float2 numq = cmulc(d, Ov);
     const float A1 = oa2 + p.delta1;
-    const float sq = __fdividef(sqrt_fast(oa2) * p.support[t], fmaf(A1, A1, kd1 * kd1));
+    const float sq = sqrt_fast(oa2) * p.support[t] * rcp_fast(fmaf(A1, A1, kd1 * kd1));
     Q[t] = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
   }
 }

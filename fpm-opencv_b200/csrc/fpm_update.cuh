@@ -106,6 +106,9 @@ __device__ __forceinline__ float half_warp_max(float v, int lane) {
 }
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// 1/x (MUFU.RCP; the denominators of the update steps are (|.|^2 + delta)^2 + (kappa delta)^2 >= delta^2 > 0, far from the
+// range where __fdividef has to rescale -- its range checks cost ~6 instructions per quotient)
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -698,7 +701,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
             const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
             const float2 num = cmulc(d, Pv);
             const float A = pa2 + p.delta2;
-            const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
+            const float sc = sqrt_fast(pa2) * inv_pmax * rcp_fast(fmaf(A, A, kd2 * kd2));
             const float2 On = make_float2(O.x + (num.x * A + num.y * kd2) * sc, O.y + (num.y * A - num.x * kd2) * sc);
             if constexpr (Q_SMEM) {
               Oc[ir * OCP + jc] = On;        // the whole box goes back to the spectrum with one TMA store after the barrier
@@ -715,7 +718,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
             const float oa2 = fmaf(O.x, O.x, O.y * O.y);
             const float2 numq = cmulc(d, O);
             const float A1 = oa2 + p.delta1;
-            const float sq = __fdividef(sqrt_fast(oa2) * sup, fmaf(A1, A1, kd1 * kd1));
+            const float sq = sqrt_fast(oa2) * sup * rcp_fast(fmaf(A1, A1, kd1 * kd1));
             Qref(iw, jw) = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
           }
           ir += qNT; jc += rNT;

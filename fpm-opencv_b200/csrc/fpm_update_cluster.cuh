@@ -450,14 +450,14 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
               const float pa2 = fmaf(Pv.x, Pv.x, Pv.y * Pv.y);
               const float2 num = cmulc(d, Pv);
               const float A = pa2 + p.delta2;
-              const float sc = __fdividef(sqrt_fast(pa2) * inv_pmax, fmaf(A, A, kd2 * kd2));
+              const float sc = sqrt_fast(pa2) * inv_pmax * rcp_fast(fmaf(A, A, kd2 * kd2));
               const float2 On = make_float2(O.x + (num.x * A + num.y * kd2) * sc, O.y + (num.y * A - num.x * kd2) * sc);
               wr[(size_t)ir * L + lane_c] = On;
               a2n = fmaf(On.x, On.x, On.y * On.y);
               const float oa2 = fmaf(O.x, O.x, O.y * O.y);
               const float2 numq = cmulc(d, O);
               const float A1 = oa2 + p.delta1;
-              const float sq = __fdividef(sqrt_fast(oa2) * Sc[e], fmaf(A1, A1, kd1 * kd1));
+              const float sq = sqrt_fast(oa2) * Sc[e] * rcp_fast(fmaf(A1, A1, kd1 * kd1));
               Qc[e] = make_float2((numq.x * A1 + numq.y * kd1) * sq, (numq.y * A1 - numq.x * kd1) * sq);
             }
             W[ir * CPC + lane_c] = a2n;

@@ -43,10 +43,6 @@
 
 namespace fpm {
 
-// 1/x (MUFU.RCP; the denominators of the update steps are (|.|^2 + delta)^2 + (kappa delta)^2 >= delta^2 > 0, far from the
-// range where __fdividef has to rescale)
-__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
 // acc + a * w for a table entry t = (w.x, w.y, -w.y, w.x)
 __device__ __forceinline__ float2 cfma4(float2 acc, float2 a, float4 t) {
   return __ffma2_rn(make_float2(a.y, a.y), make_float2(t.z, t.w), __ffma2_rn(make_float2(a.x, a.x), make_float2(t.x, t.y), acc));
@@ -502,11 +498,9 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_phased_kernel(const __grid_c
         eraw[k] = make_float2(0.f, 0.f);
         if (it < NR && evalid) eraw[k] = __ldcg(objFc + (size_t)(r0 + it) * L + wc0 + ecw);
       }
-      float pm2;
-      {
-        pm2 = warp_max(redP[lane]);
-      }
-      const float inv_pmax = rsqrt_fast(pm2);                        // 1 / max|P|
+      // (1 / max|P| is known since the barrier after phase A; computed there it costs a register through phase B:
+      //  neutral at N = 128, -3 % at N = 64)
+      const float inv_pmax = rsqrt_fast(warp_max(redP[lane]));
       FPM_TICK(13);
 
       // one element: (ir, jc) of the bbox; on == false lanes compute on element 0 and store nothing
