@@ -224,6 +224,8 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import fpmb200
+    if os.environ.get("FPM_LIB"):
+        fpmb200.lib_path = lambda: os.path.join(fpmb200.LIB_DIR, os.environ["FPM_LIB"])
     import sharding
     import synth
 
@@ -318,7 +320,11 @@ def run_b200(args):
     # runs the identical copy schedule without the reconstruction (copy-only leg); `d2h=False` drops the read-back.
     state = {"computed": [None] * n_chunks, "fetched": [None] * n_chunks}
 
-    def step_e2e(compute=True, d2h=True, sub=sub, n_in=n_in):
+    diag_ev = [] if os.environ.get("FPM_E2E_DIAG") else None
+    diag_up = []
+
+
+    def step_e2e(compute=True, d2h=True, sub=sub, n_in=n_in, h2d=True):
         computed, fetched = state["computed"], state["fetched"]
         if computed[0] is None:                    # first step of a leg: uploads start after whatever main has queued so far
             start = torch.cuda.Event()
@@ -335,7 +341,14 @@ def run_b200(args):
                 si = s_ins[(c * ((n + sub - 1) // sub) + k) % n_in]
                 if computed[c] is not None:
                     si.wait_event(computed[c])
-                ctx.upload_stack_ptr(b, min(sub, a + n - b), in_buf.ptr + b * in_bytes, si.cuda_stream)
+                if h2d:
+                    if diag_ev is not None:
+                        u0, u1 = ev(), ev()
+                        u0.record(si)
+                    ctx.upload_stack_ptr(b, min(sub, a + n - b), in_buf.ptr + b * in_bytes, si.cuda_stream)
+                    if diag_ev is not None:
+                        u1.record(si)
+                        diag_up.append((u0, u1))
             for si in s_ins:
                 e_in = torch.cuda.Event()
                 e_in.record(si)
@@ -344,7 +357,13 @@ def run_b200(args):
                 main.wait_event(fetched[c])
             if compute:
                 ctx.init_tiles(a, n, 1, sp)
+                if diag_ev is not None:
+                    d0, d1 = ev(), ev()
+                    d0.record(main)
                 ctx.run(iters, a, n, sp)
+                if diag_ev is not None:
+                    d1.record(main)
+                    diag_ev.append((d0, d1))
                 ctx.finalize(a, n, sp)
             e_c = torch.cuda.Event()
             e_c.record(main)
@@ -382,6 +401,18 @@ def run_b200(args):
     ms_e2e = timed_e2e(args.steps, max(1, args.warmup // 2))
     e2e_value = world * updates_per_step_rank / (ms_e2e * 1e-3)
     checksum = float(np.abs(hout[:: max(1, tiles // 8), :4096]).sum())
+    if os.environ.get("FPM_E2E_DIAG"):       # developer: which leg of the pipeline costs what (stderr)
+        for lab, kw in (("compute chunked, no copies", dict(h2d=False, d2h=False)), ("compute + D2H", dict(h2d=False)),
+                        ("compute + H2D", dict(d2h=False)), ("all", dict())):
+            del diag_ev[:]
+            del diag_up[:]
+            t_leg = timed_e2e(4, 2, **kw)
+            if diag_up:
+                ups = [a.elapsed_time(b) for a, b in diag_up[-4 * n_chunks:]]
+                print("e2e diag: %-28s upload call (copy + conversion) on its stream %.2f ms (min %.2f max %.2f)" % (lab, np.mean(ups), min(ups), max(ups)), file=sys.stderr)
+            runs = [a.elapsed_time(b) for a, b in diag_ev[-4 * n_chunks:]]
+            print("e2e diag: %-28s %.2f ms/step; update kernel per chunk %.2f ms (min %.2f max %.2f), sum %.2f" % (
+                lab, t_leg, np.mean(runs), min(runs), max(runs), np.sum(runs) / 4), file=sys.stderr)
     # the same copies with no reconstruction in between: what the host link alone allows
     ms_copy = timed_e2e(3, 1, compute=False)
     ms_h2d = timed_e2e(3, 1, compute=False, d2h=False)

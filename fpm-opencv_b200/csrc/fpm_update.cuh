@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
           for (int m = 0; m < R1; ++m) {
             const int i = i0 + R2 * m;
             const int iw = (i < H) ? i : i - N;
-            const int iwc = min(max(iw, p.ylo), p.yhi);
-            v[m] = wbase[iwc * L + jw];
+            const int iwc = min(max(iw, p.ylo), p.yhi);             // (clamped, unconditional: predicated loads of the in-box
+            v[m] = wbase[iwc * L + jw];                              //  rows only were slower, 10.2 k against 6.9 k cycles)
           }
 #pragma unroll
           for (int m = 0; m < R1; ++m) {
@@ -665,9 +665,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
           if (it < NR && evalid) eraw[k] = __ldcg(objFc + (size_t)(r0 + it) * L + wc0 + ecw);
         }
       }
-      float pm2 = red[32];
-#pragma unroll
-      for (int w = 1; w < NW; ++w) pm2 = fmaxf(pm2, red[32 + w]);
+      const float pm2 = warp_max(red[32 + (lane % NW)]);                       // (one load + REDUX instead of NW dependent loads)
       const float inv_pmax = rsqrt_fast(pm2);                                  // 1 / max|P|
       FPM_TICK(14);
       const int n = NR * NC;
@@ -713,6 +711,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
             }
             const float a2n = fmaf(On.x, On.x, On.y * On.y);
             if constexpr (Q_SMEM) W[((r0 + ir - rt0) << wsh) + (c0 + jc - wc0)] = a2n;
+            // (measured without these atomics: 10.5 k instead of 11.4 k cycles for the 85 x 85 box -- they are not what binds)
             else atomicMax(&Tm[(((r0 + ir) >> p.cs) - cr0) * tmc + (((c0 + jc) >> 4) - cc0)], __float_as_uint(a2n));
             // Q = d * |O| conj(O) / ((|O|^2 + delta1) + i*kappa*delta1) * support   (fpmMain.cpp:459-472, O before the update)
             const float oa2 = fmaf(O.x, O.x, O.y * O.y);
@@ -812,9 +811,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
     __syncthreads();
     FPM_TICK(9);
     {
-      float om2 = red[0];
-#pragma unroll
-      for (int w = 1; w < NW; ++w) om2 = fmaxf(om2, red[w]);
+      const float om2 = warp_max(red[lane % NW]);
       inv_objf_max = rsqrt_fast(om2);                // applied to P by the next S1 (or by the epilogue below)
     }
     if constexpr (!Q_SMEM) {
@@ -902,9 +899,20 @@ __global__ void __launch_bounds__(256) stack_convert_kernel(float* stack, const 
   const int band = blockIdx.y;                                              // rows [band*RB, +RB): y / R1 = band*NQ + yq
   const uint16_t* src = raw + ((size_t)(first_image + blockIdx.x) * N + (size_t)band * RB) * N;
   float* dst = stack + (size_t)(first_image + blockIdx.x) * N * N;
-  for (int t = threadIdx.x; t < NB / 8; t += 256) {                         // 8 pixels of one row per thread
+  constexpr int NLD = NB / 8 / 256;                                         // 16-byte loads per thread: all in flight together
+  static_assert(NB % (8 * 256) == 0, "whole rounds of loads");
+  uint4 qq[NLD];
+#pragma unroll
+  for (int r = 0; r < NLD; ++r) {
+    const int t = threadIdx.x + r * 256;
     const int yy = t / (N / 8), c = t - yy * (N / 8);
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)yy * N) + c);
+    qq[r] = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)yy * N) + c);   // (streaming: read once)
+  }
+#pragma unroll
+  for (int r = 0; r < NLD; ++r) {                                           // 8 pixels of one row per thread and round
+    const int t = threadIdx.x + r * 256;
+    const int yy = t / (N / 8), c = t - yy * (N / 8);
+    const uint4 q = qq[r];
     const unsigned w[4] = {q.x, q.y, q.z, q.w};
     const int ym = yy % R1, yq = yy / R1;
 #pragma unroll
