@@ -17,3 +17,15 @@ def test_fft_regs_host(tmp_path):
                            "-o", exe, os.path.join(ROOT, "tests", "native", "fft_regs_host_test.cu")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="nvcc not available")
+def test_phased_kernel_shared_memory_layout(tmp_path):
+    """PhasedShape<N>::layout (host code of csrc/fpm_update_phased.cuh): alignment, no overlaps, fits a B200 CTA."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "phased_layout_host_test")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-I",
+                           os.path.join(ROOT, "fpm-opencv_b200", "csrc"), "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "phased_layout_host_test.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
