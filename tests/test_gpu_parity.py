@@ -464,6 +464,38 @@ def test_asymmetric_support_bbox(name, ell, unfused, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("name,ell", [("cfg2_fLEDc_np128", (3, 14.0, -5, 9.0)),      # 29 x 19 box: no full group of 32 columns
+                                      ("cfg2_fLEDc_np128", (-2, 5.0, 1, 5.0)),       # 11 x 11: a rectangle inside one or two max-cells
+                                      ("cfg2_fLEDc_np128", (8, 9.0, -6, 11.0)),      # 19 x 23, off-centre: one-sided in x
+                                      ("cfg1_mono_np64", (0, 31.0, 0, 31.0)),        # 63 x 63: every thread has a phase-A butterfly
+                                      ("cfg1_mono_np64", (-20, 10.0, 0, 31.0)),      # off-centre, tall
+                                      ("cfg1_mono_np64", (0, 4.0, 0, 4.0))])
+def test_phased_kernel_box_shapes(name, ell):
+    """fpm_update_phased_kernel over the shapes its work decomposition distinguishes (column groups of 32 + packed
+    left-overs in the column B stages and in phase C, dedicated / shared threads for the max-cell rebuild, one to five
+    touched cell columns), with windows at the spectrum border among the LEDs; 2 passes against the oracle."""
+    c = T.Case(name, 6, 14)
+    N = c.N
+    c.cx[10:14] = np.array([0, c.L - N, 3, c.L - N - 1], np.int16)
+    c.cy[10:14] = np.array([0, c.L - N, c.L - N - 2, 1], np.int16)
+    y, x = np.mgrid[0:N, 0:N]
+    yw, xw = np.where(y < N // 2, y, y - N), np.where(x < N // 2, x, x - N)
+    x0, ax, y0, ay = ell
+    S = ((((xw - x0) / ax) ** 2 + ((yw - y0) / ay) ** 2) <= 1).astype(np.float32)
+    ctx = c.make_ctx(support=S, cluster=1)
+    assert "fpm_update_phased_kernel" in ctx.variant, ctx.variant
+    st = orc.State(orc.init_state(c.stack, c.L, c.r).objFc, S.astype(np.complex128), S.astype(np.float64))
+    ctx.upload_state(0, T.corner(st.objFc), st.P)
+    for _ in range(2):
+        for k in range(len(c.cx)):
+            orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+    ctx.run(2)
+    ctx.finalize()
+    e = compare(ctx, st)
+    note("three-phase kernel %s support %s: rel-L2 objF %.2e pupil %.2e [%s]" % (name, ell, e[0], e[1], ctx.variant[:100]))
+    ctx.close()
+
+
 @pytest.mark.parametrize("name", ["cfg1_mono_np64", "cfg7_mono_np90"])
 def test_windows_touching_the_spectrum_border(name):
     """Crop origins 0 and Nlarge-Np (the legal extremes, fpmMain.cpp:157-165)."""
