@@ -60,7 +60,7 @@ struct UpdateParams {
   int ocp;                  // row pitch (float2) of the on-chip window copies: even and >= NC+1 (TMA boxes start on 16 B)
   int cs;                   // log2 rows per max-cell (cells are (1<<cs) rows x 16 columns)
   long long* stage_clk;     // [16] per-stage cycle totals of CTA 0 (only with -DFPM_STAGE_TIMING)
-  int noff[12];             // fpm_update_narrow_kernel: byte offsets of its box-dependent shared-memory arrays (NarrowShape::layout)
+  int noff[12];             // fpm_update_phased_kernel: byte offsets of its box-dependent shared-memory arrays (PhasedShape::layout)
 };
 
 template <int N> struct Shape {
