@@ -51,26 +51,30 @@ __global__ void __launch_bounds__(256) plan_fft_kernel(const __grid_constant__ P
   constexpr int h = L / 2;
 
   for (int t = tid; t < L; t += NT) tw[t] = p.tw[t];
-  if (!p.cols) {
-    // rows: lanes along the line (coalesced); element n of line l sits at l*PITCH + n + n/M0
-    for (int t = tid; t < LINES * L; t += NT) {
-      const int l = t / L, n = t - l * L;
-      float2 v = make_float2(0.f, 0.f);
-      if (line0 + l < L) {
+  // element n of line l sits at l*PITCH + n + n/M0.  Rows: lanes along the line (coalesced); columns: lanes along 16
+  // adjacent columns (16 x 8 bytes contiguous per row).  LB global loads of a thread are in flight together.
+  constexpr int LB = 8, NLOAD = (LINES * L + NT - 1) / NT;
+  for (int b = 0; b < NLOAD; b += LB) {
+    float2 v[LB];
+    int so[LB];
+#pragma unroll
+    for (int k = 0; k < LB; ++k) {
+      const int t = tid + (b + k) * NT;
+      int l, n;
+      if (!p.cols) { l = t / L; n = t - l * L; } else { l = t % LINES; n = t / LINES; }
+      const bool in = (b + k < NLOAD) && t < LINES * L && line0 + l < L;
+      so[k] = (b + k < NLOAD && t < LINES * L) ? l * PITCH + n + n / M0 : -1;
+      size_t g;
+      if (!p.cols) {
         int r = line0 + l, c = n;
         if (p.shift) { r += h; if (r >= L) r -= L; c += h; if (c >= L) c -= L; }
-        v = src[(size_t)r * L + c];
-      }
-      buf[l * PITCH + n + n / M0] = v;
+        g = (size_t)r * L + c;
+      } else g = (size_t)n * L + line0 + l;
+      v[k] = in ? __ldcs(src + g) : make_float2(0.f, 0.f);
     }
-  } else {
-    // columns: lanes along adjacent columns (16 x 8 bytes contiguous per row)
-    for (int t = tid; t < LINES * L; t += NT) {
-      const int l = t % LINES, n = t / LINES;
-      float2 v = make_float2(0.f, 0.f);
-      if (line0 + l < L) v = src[(size_t)n * L + line0 + l];
-      buf[l * PITCH + n + n / M0] = v;
-    }
+#pragma unroll
+    for (int k = 0; k < LB; ++k)
+      if (so[k] >= 0) buf[so[k]] = v[k];
   }
   __syncthreads();
 
