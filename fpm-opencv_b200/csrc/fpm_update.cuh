@@ -924,11 +924,14 @@ __global__ void __launch_bounds__(256) stack_convert_kernel(float* stack, const 
     }
   }
   __syncthreads();
-  for (int lo = threadIdx.x; lo < NB; lo += 256) {
+  static_assert(RUN % 4 == 0 && NB % (4 * 256) == 0, "16-byte stores");
+  for (int lo = 4 * threadIdx.x; lo < NB; lo += 4 * 256) {                  // four consecutive floats of a run per store
     const int r = lo / RUN, within = lo - r * RUN;
     const int A = r / R1, ym = r - A * R1;                                  // A = x % R1
     // stack_offset<N>(y, x) = ((x % R1) * N + R2 * (y % R1) + y / R1) * R2 + x / R1, with y / R1 = band*NQ + within / R2
-    dst[((size_t)A * N + R2 * ym + band * CS::NQ) * R2 + within] = buf[pad(lo)];
+    const int pl = pad(lo);                                                 // (a group of four never crosses a pad)
+    const float4 v = make_float4(buf[pl], buf[pl + 1], buf[pl + 2], buf[pl + 3]);
+    __stcs(reinterpret_cast<float4*>(dst + ((size_t)A * N + R2 * ym + band * CS::NQ) * R2 + within), v);
   }
 }
 
