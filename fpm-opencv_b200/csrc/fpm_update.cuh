@@ -54,6 +54,8 @@ struct UpdateParams {
   float2* field_gmem;       // [n_tiles][N][N+1] scratch when the field does not fit shared memory
   int L, n_leds;
   int tile0;                // first tile of this launch
+  const int* tile_list;     // when set: CTA b works on tile tile_list[b] & 0x3fffffff (balanced passes, fpmb200_run); else tile0 + b
+  float* ucache;            // fpm_update_phased_kernel: [n_tiles][L][L/16] cell maxima handed from pass to pass (or NULL)
   int slot_begin, n_updates;
   float delta1, delta2, eps, kappa;
   int ylo, yhi, xlo, xhi;   // support bbox (wrapped)
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(NT, MINB) fpm_update_kernel(const __grid_const
   extern __shared__ __align__(1024) unsigned char smem_raw[];   // TMA destinations need 128-byte alignment
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = p.tile0 + blockIdx.x;
+  const int tile = p.tile_list ? (p.tile_list[blockIdx.x] & 0x3fffffff) : p.tile0 + blockIdx.x;
   const int L = p.L;
   const int NR = p.yhi - p.ylo + 1, NC = p.xhi - p.xlo + 1;
   const int gc = L >> 4, gr = L >> p.cs;                 // max-cells are (1<<cs) rows x 16 columns

@@ -104,7 +104,11 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_phased_kernel(const __grid_c
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = warp / WPB, gsub = warp % WPB;
-  const int tile = p.tile0 + blockIdx.x;
+  // balanced passes (fpmb200_run): tile from a list; bit 30 of the entry = the cell maxima this kernel left in p.ucache at
+  // the end of the tile's previous pass are current
+  const int tile_entry = p.tile_list ? p.tile_list[blockIdx.x] : p.tile0 + blockIdx.x;
+  const int tile = tile_entry & 0x3fffffff;
+  const bool u_cached = p.ucache && (tile_entry & 0x40000000);
   const int L = p.L;
   const int NR = p.yhi - p.ylo + 1, NC = p.xhi - p.xlo + 1;
   const int gc = L >> 4, gc4 = gc >> 2;                    // max-cells are 1 row x 16 columns (cs == 0); float4 per U row
@@ -184,6 +188,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_phased_kernel(const __grid_c
     Sc[t] = in ? p.support[gi] : 0.f;
     Qc[t] = make_float2(0.f, 0.f);
   }
+  if (u_cached) {                                           // U as the previous pass over this tile left it
+    const float4* src = reinterpret_cast<const float4*>(p.ucache + (size_t)tile * L * gc);
+    for (int t = tid; t < L * gc4; t += NT) reinterpret_cast<float4*>(U)[t] = __ldcg(src + t);
+  } else
   for (int it = warp; it < L * (L >> 5); it += NW) {       // U from the spectrum: one warp per pair of cells
     const int row = it / (L >> 5), seg = it % (L >> 5);
     const float2 o = objFc[(size_t)row * L + (seg << 5) + lane];
@@ -603,6 +611,23 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_phased_kernel(const __grid_c
       const float2 Pn = cfma(inv_objf_max, Qc[t], Pc[t]);
       if (jc < NC) Pg[((p.ylo + ir) & (N - 1)) * N + ((p.xlo + jc) & (N - 1))] = Pn;
     }
+  }
+  if (p.ucache) {
+    // leave the cell maxima for the tile's next pass: the cells of the last rectangle are still to be rebuilt from W
+    if (p.n_updates > 0) {
+      const int pwsh = 32 - __clz((pr_ncc << 4) - 1);
+      for (int t = tid; t < NR * pr_ncc; t += NT) {
+        const int a = t / pr_ncc, b = t - a * pr_ncc;
+        const float4* w4 = reinterpret_cast<const float4*>(W + (a << pwsh) + (b << 4));
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float4 v = w4[q]; m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w)); }
+        U[(pr_r0 + a) * gc + pr_cc0 + b] = m;
+      }
+    }
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(p.ucache + (size_t)tile * L * gc);
+    for (int t = tid; t < L * gc4; t += NT) dst[t] = reinterpret_cast<const float4*>(U)[t];
   }
 }
 

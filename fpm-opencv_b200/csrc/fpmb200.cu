@@ -100,6 +100,11 @@ struct fpmb200_ctx {
   float* mosaic_dev = nullptr;
   size_t mosaic_elems = 0;
   cudaEvent_t events[64] = {};  // stream markers of fpmb200_event_record
+  int* sched_dev = nullptr;    // tile lists of the balanced passes of fpmb200_run ...
+  size_t sched_cap = 0;
+  int sched_first = -1, sched_n = 0, sched_iters = 0;   // ... cached for this (first, n, iters)
+  std::vector<int> sched_counts;
+  float* ucache = nullptr;     // [n_tiles][L][L/16]: cell maxima of fpm_update_phased_kernel between balanced passes
   int cluster_req = 0;         // CTAs per tile asked for (0 = choose)
   int cluster = 1;             // CTAs per tile in use (1 = fpm_update_kernel, >1 = fpm_update_cluster_kernel)
   int cpc = 0;                 // bbox columns per CTA of the cluster kernel
@@ -153,6 +158,8 @@ static void drop_graphs(fpmb200_ctx* c);
 static void free_tiles(fpmb200_ctx* c) {
   drop_graphs(c);
   cudaFree(c->objFc); cudaFree(c->objCrop); cudaFree(c->pupil); cudaFree(c->stack); cudaFree(c->raw); cudaFree(c->support);
+  cudaFree(c->sched_dev); c->sched_dev = nullptr; c->sched_cap = 0; c->sched_first = -1;
+  cudaFree(c->ucache); c->ucache = nullptr;
   cudaFree(c->crop); cudaFree(c->twN); cudaFree(c->twL); cudaFree(c->field_gmem); cudaFree(c->scratch);
   cudaFree(c->gfield); cudaFree(c->gq); cudaFree(c->gcells); cudaFree(c->gscal);
   cudaFree(c->origins); cudaFree(c->frame_dev); cudaFree(c->bg_dev); cudaFree(c->mosaic_dev);
@@ -925,14 +932,15 @@ static int run_updates_general(fpmb200_ctx* c, int first, int n, int slot_begin,
   return FPMB200_OK;
 }
 
-static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st) {
+static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_updates, cudaStream_t st, const int* tile_list = nullptr,
+                       float* ucache = nullptr) {
   if (!c->have_support || !c->have_leds) return fail(FPMB200_ERR_STATE, "upload LED tables and the pupil support first");
   if (c->general) { CK(cudaSetDevice(c->device)); return run_updates_general(c, first, n, slot_begin, n_updates, st); }
   UpdateParams p;
   memset(&p, 0, sizeof p);
   p.objFc = c->objFc; p.pupil = c->pupil; p.stack = c->stack; p.support = c->support; p.crop = c->crop;
   p.tw = c->twN; p.field_gmem = c->field_gmem; p.L = c->L; p.n_leds = c->n_leds; p.tile0 = first;
-  p.slot_begin = slot_begin; p.n_updates = n_updates;
+  p.slot_begin = slot_begin; p.n_updates = n_updates; p.tile_list = tile_list; p.ucache = ucache;
   p.delta1 = c->delta1; p.delta2 = c->delta2; p.eps = c->eps; p.kappa = c->kappa;
   p.ylo = c->ylo; p.yhi = c->yhi; p.xlo = c->xlo; p.xhi = c->xhi; p.cs = c->cs; p.ocp = c->ocp;
   if (c->have_tmap) p.tmap = c->tmap;
@@ -965,7 +973,61 @@ extern "C" int fpmb200_run(fpmb200_ctx* c, int first, int n, int iters, void* st
   if (rc) return rc;
   if (iters < 0) return fail(FPMB200_ERR_ARG, "iters < 0");
   if (iters == 0) return FPMB200_OK;
-  return run_updates(c, first, n, 0, iters * c->n_leds, stream ? (cudaStream_t)stream : c->stream);
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  // One persistent CTA per tile runs all iterations; with more tiles than SMs the last wave is partly empty (320 tiles =
+  // 148 + 148 + 24: the third wave leaves 124 SMs idle for a third of the run).  Tiles are independent and an iteration
+  // boundary is a clean cut (the launch-to-launch state is objFc / pupil in global memory: "steps == run", bit for bit),
+  // so the run is re-cut into passes of ONE iteration over at most sm_count tiles, tiles with the most iterations left
+  // first: max(iters, ceil(n * iters / sm_count)) passes instead of ceil(n / sm_count) * iters.  Each pass pays the
+  // kernel's prologue again (cell maxima from the spectrum, pupil, first windows: a few per cent of an iteration).
+  // FPMB200_RUN_BALANCED=0 keeps the single launch.
+  const int S = c->sm_count;
+  const char* e = getenv("FPMB200_RUN_BALANCED");
+  if (!c->general && c->cluster == 1 && n > S && iters >= 2 && !(e && e[0] == '0')) {
+    const long long waves = (long long)((n + S - 1) / S) * iters;
+    const long long passes = std::max<long long>(iters, ((long long)n * iters + S - 1) / S);
+    if (passes * 21 < waves * 20) {                          // worth at least the 5 % the extra prologues may cost
+      CK(cudaSetDevice(c->device));
+      if (c->sched_first != first || c->sched_n != n || c->sched_iters != iters) {       // (re)build and upload the schedule
+        std::vector<int> left(n, iters), lists, order(n);
+        c->sched_counts.clear();
+        for (long long done = 0; done < (long long)n * iters;) {
+          // tiles with the most iterations left first (stable: lower index first)
+          for (int t = 0; t < n; ++t) order[t] = t;
+          std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return left[a] > left[b]; });
+          int cnt = 0;
+          for (int k = 0; k < n && cnt < S; ++k)
+            if (left[order[k]] > 0) {
+              // bit 30: not the tile's first pass of this run -- the phased kernel finds its cell maxima in c->ucache
+              lists.push_back((first + order[k]) | (left[order[k]] < iters ? 0x40000000 : 0));
+              --left[order[k]]; ++cnt;
+            }
+          c->sched_counts.push_back(cnt);
+          done += cnt;
+        }
+        c->sched_first = -1;
+        CK(cudaDeviceSynchronize());                         // earlier passes (on any stream) may still read the old lists
+        if (lists.size() > c->sched_cap) {
+          cudaFree(c->sched_dev); c->sched_dev = nullptr; c->sched_cap = 0;
+          CK(cudaMalloc(&c->sched_dev, sizeof(int) * lists.size()));
+          c->sched_cap = lists.size();
+        }
+        CK(cudaMemcpyAsync(c->sched_dev, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        c->sched_first = first; c->sched_n = n; c->sched_iters = iters;
+      }
+      if (c->phased && !c->ucache)
+        CK(cudaMalloc(&c->ucache, sizeof(float) * (size_t)c->n_tiles * c->L * (c->L >> 4)));
+      const std::vector<int>& counts = c->sched_counts;
+      size_t off = 0;
+      for (int cnt : counts) {
+        if ((rc = run_updates(c, first, cnt, 0, c->n_leds, st, c->sched_dev + off, c->phased ? c->ucache : nullptr))) return rc;
+        off += cnt;
+      }
+      return FPMB200_OK;
+    }
+  }
+  return run_updates(c, first, n, 0, iters * c->n_leds, st);
 }
 
 extern "C" int fpmb200_step(fpmb200_ctx* c, int tile, int led_slot) {

@@ -551,6 +551,28 @@ def test_steps_equal_run_bitwise():
     a.close(), b.close()
 
 
+def test_balanced_passes_equal_one_launch(monkeypatch):
+    """More tiles than SMs, not a multiple: fpmb200_run re-cuts the run into passes of one iteration over at most
+    sm_count tiles (tiles with the most iterations left first) instead of leaving the last wave partly empty.  An
+    iteration boundary is a clean cut, so the results equal the single persistent launch bit for bit."""
+    c = T.Case("cfg1_mono_np64", 9, 12)
+    n_tiles, iters = 150, 3
+    out = {}
+    for bal in ("0", "1"):
+        monkeypatch.setenv("FPMB200_RUN_BALANCED", bal)
+        ctx = c.make_ctx(n_tiles=n_tiles)
+        l0 = ctx.kernel_launches
+        ctx.run(iters)
+        out[bal] = (ctx.kernel_launches - l0, [ctx.download(t, objCrop=False) for t in (0, 1, 147, 148, 149)])
+        ctx.close()
+    assert out["0"][0] == 1 and out["1"][0] > 1, (out["0"][0], out["1"][0])
+    for ta, tb in zip(out["0"][1], out["1"][1]):
+        for a, b in zip(ta, tb):
+            if a is not None:
+                assert np.array_equal(a, b)
+    note("balanced passes: %d tiles x %d iterations in %d launches, bit-identical to the single launch" % (n_tiles, iters, out["1"][0]))
+
+
 def test_tiles_are_independent_and_deterministic():
     """Many tiles in one launch (more CTAs than fit at once): identical inputs give identical bits in
     every slot, different inputs do not interfere -- the property the multi-GPU sharding relies on."""
