@@ -81,7 +81,10 @@ int fpmb200_upload_stack(fpmb200_ctx* ctx, int tile_first, int n, const uint16_t
 int fpmb200_init_tiles(fpmb200_ctx* ctx, int tile_first, int n, int init_led_slot, void* stream);
 
 /* `iters` passes of the inner loops fpmMain.cpp:345-476 over all LED slots, sequential order
- * preserved, for tiles [tile_first, tile_first+n).  Asynchronous on `stream`. */
+ * preserved, for tiles [tile_first, tile_first+n).  Asynchronous on `stream`.  Pass all iterations in
+ * one call when there are more tiles than SMs: the run is then cut into balanced passes of one
+ * iteration over at most sm_count tiles instead of leaving the last wave partly empty (same results,
+ * bit for bit; FPMB200_RUN_BALANCED=0 keeps one launch). */
 int fpmb200_run(fpmb200_ctx* ctx, int tile_first, int n, int iters, void* stream);
 
 /* One sub-aperture update (fpmMain.cpp:350-475) of one tile; for per-step parity. */
