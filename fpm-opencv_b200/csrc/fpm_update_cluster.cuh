@@ -35,7 +35,33 @@ __device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rb
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
                ::"r"(raddr), "f"(v), "r"(rbar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+#ifdef FPM_CL_DEBUG
+// developer build: a wait that gives up after 2^25 polls and says which barrier of which update never completed
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int id = -1, int u = -1) {
+  __syncwarp();
+  uint32_t bad;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .pred q;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "WAITD_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra DONED_%=;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.gt.u32 q, n, 0x2000000;\n\t"
+      "@!q bra WAITD_%=;\n\t"
+      "mov.u32 %0, 1;\n\t"
+      "DONED_%=:\n\t}" : "=r"(bad) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  if (bad) {
+    if ((threadIdx.x & 31) == 0) printf("mbarrier %d never completed: update %d block %d warp %d parity %u\n", id, u, blockIdx.x, threadIdx.x >> 5, parity);
+    __trap();
+  }
+}
+#else
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int = -1, int = -1) {   // acquire at cluster scope
+  // Whole warps wait.  The warp reconverges first: lanes that skipped the preceding column stage must not spin here
+  // while their siblings still have the remote stores to issue that this (or a peer's) barrier is waiting for.
+  __syncwarp();
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAITC_%=:\n\t"
@@ -44,6 +70,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       "bra WAITC_%=;\n\t"
       "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#endif
 // relaxed: the caller issues ONE fence.acq_rel.cluster before a batch of these (a .release arrive costs a
 // MEMBAR.ALL.GPU each)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {
@@ -52,9 +79,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {
 
 // Shared-memory carve-up, identical in every CTA of the cluster (DSMEM addresses are rank-mapped offsets).
 template <int N, int C> struct ClusterLayout {
-  size_t rslab, cslab, twA, twB, Pc, Qc, Sc, U, Tm, red, pmx, omx, bars, total;
+  size_t rslab, cslab, twA, twB, Pc, Qc, Sc, Wb, U, Tm, red, pmx, omx, bars, total;
   int gro, tmr, tmc;
-  __host__ __device__ ClusterLayout(int NR, int NC, int CPC, int L, int cs) {
+  // ws (narrow boxes on 128 x 128 tiles, the SIX instances of the kernel): this CTA's column slice of the window stays in
+  // shared memory, double-buffered (see "window slice" below).  Wide boxes read the slice from the spectrum (L2) in S1
+  // and C2: at N = 256 the slabs leave no room for it, and at N = 128 forwarding a wide rectangle element by element
+  // costs more than the loads it saves (85 x 85 box on four CTAs: 12.2 us per update with the slice on chip, 11.3 without).
+  __host__ __device__ ClusterLayout(int NR, int NC, int CPC, int L, int cs, bool ws) {
     using S = Shape<N>;
     size_t o = 0;
     rslab = o; o += (sizeof(float2) * (N / C) * S::PITCH + 15) / 16 * 16;
@@ -64,6 +95,7 @@ template <int N, int C> struct ClusterLayout {
     Pc = o; o += (sizeof(float2) * NR * CPC + 15) / 16 * 16;
     Qc = o; o += (sizeof(float2) * NR * CPC + 15) / 16 * 16;
     Sc = o; o += (sizeof(float) * NR * CPC + 15) / 16 * 16;
+    Wb = o; o += ws ? 2 * ((sizeof(float2) * NR * CPC + 15) / 16 * 16) : 0;
     gro = ((L >> cs) + C - 1) / C;                      // cell rows per CTA
     U = o; o += (sizeof(float) * gro * (L >> 4) + 15) / 16 * 16;
     tmr = (NR >> cs) + 2; tmc = (NC >> 4) + 2;
@@ -71,16 +103,21 @@ template <int N, int C> struct ClusterLayout {
     red = o; o += sizeof(float) * 64;
     pmx = o; o += sizeof(float) * 16;
     omx = o; o += sizeof(float) * 16;
-    bars = o; o += sizeof(uint64_t) * 4;
+    bars = o; o += sizeof(uint64_t) * 6;
     total = o;
   }
 };
 
-template <int N, int C, int NT>
+// SIX (N = 128 only): the box lies within +-(3 * R2 - 1), so the radix-16 stage-A butterflies see 6 of their 16 samples
+// (and the stage-A' butterflies keep 6 outputs), as in fpm_update_phased_kernel.
+template <int N, int C, int NT, bool SIX = false>
 __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_constant__ UpdateParams p) {
   using S = Shape<N>;
   constexpr int R1 = S::R1, R2 = S::R2, PITCH = S::PITCH, CH = S::CH;
   constexpr int H = N / 2, NW = NT / 32;
+  static_assert(!SIX || R1 == 16, "six-sample butterflies are radix 16");
+  constexpr int NIN = SIX ? 6 : R1;                         // samples a stage-A butterfly reads
+  auto m_of = [](int k) constexpr { return SIX ? ((k < 3) ? k : R1 - 6 + k) : k; };
   constexpr int RPC = N / C;                // scrambled row positions per CTA
   constexpr int PR = N + 1;                 // cslab pitch (float2 per column): odd, lanes = columns hit distinct banks
   static_assert(RPC % R2 == 0 && RPC % 32 == 0, "a stage-B work item must not straddle two row owners");
@@ -104,7 +141,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   const int tqc = ncl ? tid / ncl : 0, trc = ncl ? tid - tqc * ncl : 0;
   const int qNTc = ncl ? NT / ncl : 0, rNTc = ncl ? NT % ncl : 0;               // t += NT without dividing
 
-  const ClusterLayout<N, C> lay(NR, NC, CPC, L, p.cs);
+  constexpr bool WS = SIX;
+  const ClusterLayout<N, C> lay(NR, NC, CPC, L, p.cs, WS);
   float2* rslab = reinterpret_cast<float2*>(smem_raw + lay.rslab);
   float2* cslab = reinterpret_cast<float2*>(smem_raw + lay.cslab);
   float2* twA = reinterpret_cast<float2*>(smem_raw + lay.twA);
@@ -122,6 +160,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   uint64_t* cbar = bars + 1;   // column slab complete
   uint64_t* ubar = bars + 2;   // every rank has merged its cell maxima (C arrivals); also orders the spectrum stores
   uint64_t* obar = bars + 3;   // every rank's grid maximum has arrived
+  uint64_t* wbar = bars + 4;   // window slice of the next update complete (the forwarded part: bytes of remote st.async)
+  const size_t wb_stride = (sizeof(float2) * NR * CPC + 15) / 16 * 16;
+  float2* const Wb0 = reinterpret_cast<float2*>(smem_raw + lay.Wb);               // window slice [NR][CPC] of even updates
+  float2* const Wb1 = reinterpret_cast<float2*>(smem_raw + lay.Wb + (WS ? wb_stride : 0));   // ... of odd updates
   float* W = reinterpret_cast<float*>(rslab);                     // |O_new|^2 on the slice; rslab is idle during C2/D
   const int tmc = lay.tmc;
 
@@ -163,10 +205,12 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     }
   }
   for (int t = tid; t < lay.tmr * lay.tmc; t += NT) Tm[t] = 0u;
+  if (tid < 64) red[tid] = 0.f;                            // (warps that only do side work never write their max|P|^2 slot)
   if (tid == 0) {
-    mbar_init(rbar, 1); mbar_init(cbar, 1); mbar_init(ubar, C); mbar_init(obar, 1);
+    mbar_init(rbar, 1); mbar_init(cbar, 1); mbar_init(ubar, C); mbar_init(obar, 1); mbar_init(wbar, 1);
   }
   const uint32_t rbar_a = smem_u32(rbar), cbar_a = smem_u32(cbar), ubar_a = smem_u32(ubar), obar_a = smem_u32(obar);
+  const uint32_t wbar_a = smem_u32(wbar);
   const uint32_t rslab_a = smem_u32(rslab), cslab_a = smem_u32(cslab), pmx_a = smem_u32(pmx), omx_a = smem_u32(omx);
   const uint32_t rbar_bytes = (uint32_t)(sizeof(float2) * RPC * NC + sizeof(float) * C);
   const uint32_t cbar_bytes = (uint32_t)(sizeof(float2) * N * ncl);
@@ -182,13 +226,30 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   long long tprev_ = clock64();
 #endif
 
+  // Window slice (WS): the columns of the window this CTA owns live in shared memory, Wb[u & 1] for update u.  The first
+  // one is read from the spectrum here.  During update u the slice of update u + 1 is assembled in the other buffer: the
+  // elements outside this update's rectangle are read from the spectrum by threads without column work (they were
+  // written at least one update ago), the elements inside it are forwarded by C2 -- each new value goes straight into
+  // the shared memory of the CTA that owns its column in the next window (st.async + that CTA's wbar).  S1 and C2 read
+  // shared memory only; the spectrum stores of C2 stay (the spectrum is the result), off the critical path.
   short2 cr_next = p.crop[p.slot_begin % p.n_leds];
+  short2 cr_next2 = p.crop[(p.slot_begin + 1) % p.n_leds];
+  if constexpr (WS) {
+    const float2* w0 = objFc + (size_t)(cr_next.y + H + p.ylo) * L + cr_next.x + H + p.xlo + jc0;
+    for (int t = tid; t < NR * CPC; t += NT) {
+      const int ir = t / CPC, jcl = t - ir * CPC;
+      Wb0[t] = (jcl < ncl) ? __ldcg(w0 + (size_t)ir * L + jcl) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+  }
   for (int u = 0; u < p.n_updates; ++u) {
     const int slot = (p.slot_begin + u) % p.n_leds;
-    const short2 cr = cr_next;
+    const short2 cr = cr_next, crn = cr_next2;
+    cr_next = cr_next2;
     {
       const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
-      cr_next = p.crop[nslot];                              // in flight during this update
+      const int nslot2 = (nslot + 1 == p.n_leds) ? 0 : nslot + 1;
+      cr_next2 = p.crop[nslot2];                            // in flight during this update
     }
     const int xs = cr.x, ys = cr.y;
     const float* __restrict__ img = stack + (size_t)slot * N * N;
@@ -201,10 +262,24 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
 #endif
 
     const uint32_t ph = (uint32_t)(u & 1);
+    // next update's rectangle, and the part of this CTA's next slice that lies inside this update's rectangle (forwarded)
+    const bool has_next = WS && (u + 1 < p.n_updates);
+    const int r0n = crn.y + H + p.ylo, c0n = crn.x + H + p.xlo;
+    const int ovr = max(0, min(r1, r0n + NR - 1) - max(r0, r0n) + 1);
+    const int ovc = (ncl > 0) ? max(0, min(c1, c0n + jc0 + ncl - 1) - max(c0, c0n + jc0) + 1) : 0;
+    float2* const Wcur = (u & 1) ? Wb1 : Wb0;
+    float2* const Wnxt = (u & 1) ? Wb0 : Wb1;
+    const uint32_t wnxt_a = smem_u32(Wnxt);
+    if constexpr (WS) {
+      // this update's slice is complete once the forwarded values of the previous C2 have landed (phase u - 1 of wbar);
+      // whole warps wait: the warps of S1 and the one that arms the barriers
+      if (u > 0 && (warp == 0 || warp * 32 < R2 * ncl)) mbar_wait_cluster(wbar, (uint32_t)((u - 1) & 1), 4, u);
+    }
     if (tid == 0) {   // arm this update's transfers (bytes may already be arriving: the counts are signed)
       mbar_expect_tx(rbar, rbar_bytes);
       mbar_expect_tx(cbar, cbar_bytes);
       mbar_expect_tx(obar, (uint32_t)(sizeof(float) * C));
+      if (has_next) mbar_expect_tx(wbar, (uint32_t)(sizeof(float2) * ovr * ovc));
     }
     if (tid < R1) {   // next LED's 1/I rows of this CTA towards L2: R1 chunks of RPC*R2 floats
       const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
@@ -221,25 +296,106 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       if (tb < ncc && a % C == rank) U[(a / C) * gc + cc0 + tb] = 0.f;
     }
 
+    // Partial maxima of the touched cells, first part: the pixels of those cells outside the rectangle, which this update
+    // does not change (shared out over the cluster): strips above / below (full width of the touched cells) and left /
+    // right (rectangle rows).  They do not depend on this update, so they are taken while the column stage B runs
+    // (threads t0, t0 + tn, ... of every CTA).
+    auto edge_maxima = [&](int t0, int tn) {
+      const int wc0 = cc0 << 4, wcols = ncc << 4, rt0 = cr0 << p.cs, rt1 = ((cr0 + ncr) << p.cs) - 1;
+      const int wl = c0 - wc0, wrt = wc0 + wcols - 1 - c1;
+      // Strip items.  When they fit one item per thread of the cluster even with padded widths (2^wsh2 for the
+      // full-width strips, 16 for the side strips) the index is split with shifts; a runtime integer division on the
+      // per-update path costs more than the idle lanes.  Large rectangles keep the dense enumeration.
+      const int wsh2 = 32 - __clz(wcols - 1), wmask = (1 << wsh2) - 1;
+      const int P1 = (r0 - rt0) << wsh2, P2 = P1 + ((rt1 - r1) << wsh2), P3 = P2 + (NR << 4), n_pad = P3 + (NR << 4);
+      const bool padded = n_pad <= C * NT;
+      const int n_top = (r0 - rt0) * wcols, n_bot = (rt1 - r1) * wcols, n_left = NR * wl, n_right = NR * wrt;
+      const int n_all = padded ? n_pad : n_top + n_bot + n_left + n_right;
+      constexpr int DU = 4;
+      for (int base = rank * tn + t0; base < n_all; base += DU * C * tn) {
+        float2 o[DU];
+        int cell[DU];
+#pragma unroll
+        for (int k = 0; k < DU; ++k) {
+          const int t = base + k * C * tn;
+          cell[k] = -1;
+          if (t < n_all) {
+            int r, c;
+            if (padded) {
+              bool ok;
+              if (t < P1) { const int cc = t & wmask; r = rt0 + (t >> wsh2); c = wc0 + cc; ok = cc < wcols; }
+              else if (t < P2) { const int s = t - P1, cc = s & wmask; r = r1 + 1 + (s >> wsh2); c = wc0 + cc; ok = cc < wcols; }
+              else if (t < P3) { const int s = t - P2, cc = s & 15; r = r0 + (s >> 4); c = wc0 + cc; ok = cc < wl; }
+              else { const int s = t - P3, cc = s & 15; r = r0 + (s >> 4); c = c1 + 1 + cc; ok = cc < wrt; }
+              if (!ok) continue;
+            } else {
+              if (t < n_top) { r = rt0 + t / wcols; c = wc0 + t % wcols; }
+              else if (t < n_top + n_bot) { const int s = t - n_top; r = r1 + 1 + s / wcols; c = wc0 + s % wcols; }
+              else if (t < n_top + n_bot + n_left) { const int s = t - n_top - n_bot; r = r0 + s / wl; c = wc0 + s % wl; }
+              else { const int s = t - n_top - n_bot - n_left; r = r0 + s / wrt; c = c1 + 1 + s % wrt; }
+            }
+            o[k] = __ldcg(objFc + (size_t)r * L + c);
+            cell[k] = ((r >> p.cs) - cr0) * tmc + ((c >> 4) - cc0);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DU; ++k)
+          if (cell[k] >= 0) atomicMax(&Tm[cell[k]], __float_as_uint(fmaf(o[k].x, o[k].x, o[k].y * o[k].y)));
+      }
+    };
+    // the part of the next window's slice that this update does not touch: spectrum -> Wnxt.  Only those elements are
+    // enumerated -- the rows of the slice outside the rectangle (all columns), then the columns outside it on the other
+    // rows -- two loads in flight per thread.
+    auto next_slice = [&](int t0, int tn) {
+      const float2* wn = objFc + (size_t)r0n * L + c0n + jc0;
+      const int dr = r0n - r0, dc = c0n + jc0 - c0;             // next-slice (rn, lc) is (rn + dr, lc + dc) of this rectangle
+      const int ra = max(0, -dr), rb = max(ra, min(NR, NR - dr));         // slice rows [ra, rb) lie inside the rectangle
+      const int la = min(ncl, max(0, -dc)), lb = max(la, min(ncl, NC - dc));   // slice columns [la, lb) likewise
+      const int wout = ncl - (lb - la);                          // columns outside per inside row
+      const int n1 = (NR - (rb - ra)) * ncl, ntot = n1 + (rb - ra) * wout;
+      auto locate = [&](int t) -> int {                          // item -> element index rn * CPC + lc
+        if (t < n1) { const int q = t / ncl, lc = t - q * ncl; return ((q < ra) ? q : q + (rb - ra)) * CPC + lc; }
+        const int t2 = t - n1, q = t2 / wout, w = t2 - q * wout;
+        return (ra + q) * CPC + ((w < la) ? w : w + (lb - la));
+      };
+      for (int t = t0; t < ntot; t += 2 * tn) {
+        const int ea = locate(t), eb = (t + tn < ntot) ? locate(t + tn) : ea;
+        const int rna = ea / CPC, rnb = eb / CPC;
+        const float2 va = __ldcg(wn + (size_t)rna * L + (ea - rna * CPC));
+        const float2 vb = __ldcg(wn + (size_t)rnb * L + (eb - rnb * CPC));
+        Wnxt[ea] = va;
+        Wnxt[eb] = vb;
+      }
+    };
+    // Threads without a column item in S1 / S2 (the same count in every CTA of the cluster) take this side work while
+    // the column stages run; the column threads meet at a named barrier between S1 and S2.
+    const int hlp0 = min(NT, (R1 * CPC + 31) & ~31), hn = NT - hlp0;
+    const bool helpers = hn >= 64;
+    if (!helpers || tid >= hlp0) {                           // (without helper threads: everybody, ahead of S1)
+      const int t0 = helpers ? tid - hlp0 : tid, tn = helpers ? hn : NT;
+      if (has_next) next_slice(t0, tn);
+      edge_maxima(t0, tn);
+    }
     // ===== S1: pending pupil update (fpmMain.cpp:470-475), Phi = O*P, cols stage A (inverse) on this CTA's columns =====
-    {
+    if (!helpers || tid < hlp0) {
       float pm2 = 0.f;
       if (tid < R2 * ncl) {                              // work items packed densely over the lanes
         const int i0 = tqc, jcl = trc;
         {
-          float2 v[R1];
-          // Branch-free: rows outside the bbox read a clamped (valid) address and are zeroed afterwards, so the R1
+          float2 w[NIN], v[R1];
+          // Branch-free: rows outside the bbox read a clamped (valid) address and are zeroed afterwards, so the
           // window loads issue back to back and the pupil work below is straight-line code.
 #pragma unroll
-          for (int m = 0; m < R1; ++m) {
-            const int i = i0 + R2 * m;
+          for (int k = 0; k < NIN; ++k) {
+            const int i = i0 + R2 * m_of(k);
             const int iw = (i < H) ? i : i - N;
             const int irc = min(max(iw - p.ylo, 0), NR - 1);
-            v[m] = wrow[irc * L + jcl];
+            if constexpr (WS) w[k] = Wcur[irc * CPC + jcl];
+            else w[k] = wrow[irc * L + jcl];
           }
 #pragma unroll
-          for (int m = 0; m < R1; ++m) {
-            const int i = i0 + R2 * m;
+          for (int k = 0; k < NIN; ++k) {
+            const int i = i0 + R2 * m_of(k);
             const int iw = (i < H) ? i : i - N;
             const bool in = (iw >= p.ylo && iw <= p.yhi);
             const int e = min(max(iw - p.ylo, 0), NR - 1) * CPC + jcl;
@@ -248,11 +404,16 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
             Pv.x = fmaf(Q.x, inv_objf_max, Pv.x);
             Pv.y = fmaf(Q.y, inv_objf_max, Pv.y);
             if (in) Pc[e] = Pv;                              // (a clamped row belongs to another work item: read only)
-            const float2 phi = cmul(v[m], Pv);
+            const float2 phi = cmul(w[k], Pv);
             pm2 = in ? fmaxf(pm2, fmaf(Pv.x, Pv.x, Pv.y * Pv.y)) : pm2;
-            v[m] = in ? phi : make_float2(0.f, 0.f);
+            w[k] = in ? phi : make_float2(0.f, 0.f);
           }
-          fftR<R1, true>(v);
+          if constexpr (SIX) fft16_in6<true>(w, v);
+          else {
+#pragma unroll
+            for (int k = 0; k < R1; ++k) v[k] = w[k];
+            fftR<R1, true>(v);
+          }
 #pragma unroll
           for (int k1 = 0; k1 < R1; ++k1) cslab[jcl * PR + i0 + R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + i0]);
         }
@@ -260,7 +421,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       pm2 = warp_max(pm2);
       if (lane == 0) red[32 + warp] = pm2;
     }
-    __syncthreads();
+    if (!helpers) __syncthreads();
+    else if (tid < hlp0) asm volatile("bar.sync 1, %0;" ::"r"(hlp0) : "memory");
     FPM_TICK(1);
     // (measured: prefetch.global.L2 of the next LED's window slice from here changes nothing, 39.7 us per update either
     //  way at Nlarge 1536 -- the window loads of S1 / C2 are not waiting for DRAM)
@@ -288,7 +450,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
 #ifdef FPM_STAGE_TIMING
     FPM_TICK(14);
 #endif
-    mbar_wait_cluster(rbar, ph);                            // row slab complete (every rank's S2 bytes have landed)
+    mbar_wait_cluster(rbar, ph, 0, u);                            // row slab complete (every rank's S2 bytes have landed)
     FPM_TICK(2);
     // 1/I of this CTA's S4 work items: issued now, consumed after S3
     constexpr int S4R = (RPC * R1 + NT - 1) / NT;
@@ -310,14 +472,20 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     for (int g = tid; g < RPC * R2; g += NT) {
       const int rl = g % RPC, j0 = g / RPC;
       float2* rp = rslab + rl * PITCH + j0;
-      float2 v[R1];
+      float2 w[NIN], v[R1];
 #pragma unroll
-      for (int m = 0; m < R1; ++m) {
+      for (int k = 0; k < NIN; ++k) {
+        const int m = m_of(k);
         const int col = j0 + R2 * m;
         const int jw = (R2 * m < H) ? col : col - N;
-        v[m] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);
+        w[k] = (jw >= p.xlo && jw <= p.xhi) ? rp[R2 * m] : make_float2(0.f, 0.f);
       }
-      fftR<R1, true>(v);
+      if constexpr (SIX) fft16_in6<true>(w, v);
+      else {
+#pragma unroll
+        for (int k = 0; k < R1; ++k) v[k] = w[k];
+        fftR<R1, true>(v);
+      }
 #pragma unroll
       for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
     }
@@ -365,7 +533,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       fftR<R1, false>(v);
       const int pos = rank * RPC + rl;
 #pragma unroll
-      for (int r = 0; r < R1; ++r) {
+      for (int k = 0; k < NIN; ++k) {                        // (the other outputs are dead code)
+        const int r = m_of(k);
         const int col = R2 * r + q;
         const int jw = (R2 * r < H) ? col : col - N;
         if (jw >= p.xlo && jw <= p.xhi) {
@@ -378,7 +547,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
 #ifdef FPM_STAGE_TIMING
     FPM_TICK(15);
 #endif
-    mbar_wait_cluster(cbar, ph);                            // column slab complete
+    mbar_wait_cluster(cbar, ph, 1, u);                            // column slab complete
     FPM_TICK(5);
     float pm2c = pmx[0];                                    // max|P|^2 over the whole pupil (all ranks' slices)
 #pragma unroll
@@ -408,7 +577,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
         for (int k1 = 0; k1 < R1; ++k1) v[k1] = cp[R2 * k1 + q];
         fftR<R1, false>(v);
 #pragma unroll
-        for (int r = 0; r < R1; ++r) {
+        for (int k = 0; k < NIN; ++k) {
+          const int r = m_of(k);
           const int i = R2 * r + q;
           const int iw = (i < H) ? i : i - N;
           if (iw >= p.ylo && iw <= p.yhi) cp[i] = v[r];
@@ -431,7 +601,8 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
           int ir = ir0, jl = jl0;
 #pragma unroll
           for (int k = 0; k < UN; ++k) {
-            Ov[k] = (base + k * NT < n) ? wr[(size_t)ir * L + jl] : make_float2(0.f, 0.f);
+            if constexpr (WS) Ov[k] = (base + k * NT < n) ? Wcur[ir * CPC + jl] : make_float2(0.f, 0.f);
+            else Ov[k] = (base + k * NT < n) ? wr[(size_t)ir * L + jl] : make_float2(0.f, 0.f);
             ir += qNT; jl += rNT;
             if (jl >= ncl) { jl -= ncl; ++ir; }
           }
@@ -453,6 +624,14 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
               const float sc = sqrt_fast(pa2) * inv_pmax * rcp_fast(fmaf(A, A, kd2 * kd2));
               const float2 On = make_float2(O.x + (num.x * A + num.y * kd2) * sc, O.y + (num.y * A - num.x * kd2) * sc);
               wr[(size_t)ir * L + lane_c] = On;
+              if constexpr (WS) {
+                // forward into the next window's slice of the CTA that owns this column there
+                const int rn = r0 + ir - r0n, cn = c0 + jc0 + lane_c - c0n;
+                if (has_next && (unsigned)rn < (unsigned)NR && (unsigned)cn < (unsigned)NC) {
+                  const int dk = (cn * cpc_inv) >> 16;                          // cn / CPC
+                  st_async_f2(mapa_u32(wnxt_a + (uint32_t)(sizeof(float2) * (rn * CPC + cn - dk * CPC)), dk), On, mapa_u32(wbar_a, dk));
+                }
+              }
               a2n = fmaf(On.x, On.x, On.y * On.y);
               const float oa2 = fmaf(O.x, O.x, O.y * O.y);
               const float2 numq = cmulc(d, O);
@@ -484,51 +663,6 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
         atomicMax(&Tm[(((r0 + ir) >> p.cs) - cr0) * tmc + (lcc0 + bl - cc0)], __float_as_uint(m));
       }
     }
-    // ... and the pixels of those cells outside the rectangle, which this update does not change (shared out over the
-    // cluster): strips above / below (full width of the touched cells) and left / right (rectangle rows)
-    {
-      const int wc0 = cc0 << 4, wcols = ncc << 4, rt0 = cr0 << p.cs, rt1 = ((cr0 + ncr) << p.cs) - 1;
-      const int wl = c0 - wc0, wrt = wc0 + wcols - 1 - c1;
-      // Strip items.  When they fit one item per thread of the cluster even with padded widths (2^wsh2 for the
-      // full-width strips, 16 for the side strips) the index is split with shifts; a runtime integer division on the
-      // per-update path costs more than the idle lanes.  Large rectangles keep the dense enumeration.
-      const int wsh2 = 32 - __clz(wcols - 1), wmask = (1 << wsh2) - 1;
-      const int P1 = (r0 - rt0) << wsh2, P2 = P1 + ((rt1 - r1) << wsh2), P3 = P2 + (NR << 4), n_pad = P3 + (NR << 4);
-      const bool padded = n_pad <= C * NT;
-      const int n_top = (r0 - rt0) * wcols, n_bot = (rt1 - r1) * wcols, n_left = NR * wl, n_right = NR * wrt;
-      const int n_all = padded ? n_pad : n_top + n_bot + n_left + n_right;
-      constexpr int DU = 4;
-      for (int base = rank * NT + tid; base < n_all; base += DU * C * NT) {
-        float2 o[DU];
-        int cell[DU];
-#pragma unroll
-        for (int k = 0; k < DU; ++k) {
-          const int t = base + k * C * NT;
-          cell[k] = -1;
-          if (t < n_all) {
-            int r, c;
-            if (padded) {
-              bool ok;
-              if (t < P1) { const int cc = t & wmask; r = rt0 + (t >> wsh2); c = wc0 + cc; ok = cc < wcols; }
-              else if (t < P2) { const int s = t - P1, cc = s & wmask; r = r1 + 1 + (s >> wsh2); c = wc0 + cc; ok = cc < wcols; }
-              else if (t < P3) { const int s = t - P2, cc = s & 15; r = r0 + (s >> 4); c = wc0 + cc; ok = cc < wl; }
-              else { const int s = t - P3, cc = s & 15; r = r0 + (s >> 4); c = c1 + 1 + cc; ok = cc < wrt; }
-              if (!ok) continue;
-            } else {
-              if (t < n_top) { r = rt0 + t / wcols; c = wc0 + t % wcols; }
-              else if (t < n_top + n_bot) { const int s = t - n_top; r = r1 + 1 + s / wcols; c = wc0 + s % wcols; }
-              else if (t < n_top + n_bot + n_left) { const int s = t - n_top - n_bot; r = r0 + s / wl; c = wc0 + s % wl; }
-              else { const int s = t - n_top - n_bot - n_left; r = r0 + s / wrt; c = c1 + 1 + s % wrt; }
-            }
-            o[k] = __ldcg(objFc + (size_t)r * L + c);
-            cell[k] = ((r >> p.cs) - cr0) * tmc + ((c >> 4) - cc0);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < DU; ++k)
-          if (cell[k] >= 0) atomicMax(&Tm[cell[k]], __float_as_uint(fmaf(o[k].x, o[k].x, o[k].y * o[k].y)));
-      }
-    }
     __syncthreads();
 #ifdef FPM_STAGE_TIMING
     FPM_TICK(12);
@@ -554,7 +688,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
 #ifdef FPM_STAGE_TIMING
     FPM_TICK(13);
 #endif
-    mbar_wait_cluster(ubar, ph);                            // every rank has merged
+    mbar_wait_cluster(ubar, ph, 2, u);                            // every rank has merged
     FPM_TICK(9);
     {
       const int nown = (gr - rank + C - 1) / C;
@@ -571,7 +705,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       m = warp_max(m);
       if (lane < C) st_async_f1(mapa_u32(omx_a + 4u * rank, lane), m, mapa_u32(obar_a, lane));
     }
-    mbar_wait_cluster(obar, ph);
+    mbar_wait_cluster(obar, ph, 3, u);
     {
       float om2 = omx[0];
 #pragma unroll

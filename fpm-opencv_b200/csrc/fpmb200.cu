@@ -330,17 +330,32 @@ extern "C" int fpmb200_upload_pupil_support(fpmb200_ctx* c, const float* mask) {
   return select_variant(c);
 }
 
+// the cluster kernel instance for this box: six-sample stage-A butterflies when a 128 x 128 tile's box lies within +-23
+typedef void (*cluster_kernel_t)(const UpdateParams);
+template <int N>
+static bool cluster_six(const fpmb200_ctx* c) {
+  const int lim = 3 * Shape<N>::R2 - 1;
+  return N == 128 && c->ylo >= -lim && c->yhi <= lim && c->xlo >= -lim && c->xhi <= lim;
+}
+template <int N, int C>
+static cluster_kernel_t cluster_kernel_for(const fpmb200_ctx* c) {
+  if constexpr (N == 128) {
+    if (cluster_six<N>(c)) return fpm_update_cluster_kernel<N, C, 512, true>;
+  }
+  return fpm_update_cluster_kernel<N, C, 512, false>;
+}
+
 template <int N, int C>
 static bool cluster_fits(fpmb200_ctx* c, int* cpc_out, int* cs_out, size_t* bytes_out, int* max_clusters = nullptr) {
   const int NR = c->yhi - c->ylo + 1, NC = c->xhi - c->xlo + 1;
   const int cpc = (NC + C - 1) / C;
   if (cpc > 32) return false;                                  // one lane per column in the column passes
   for (int cs = 0; cs <= 4; ++cs) {
-    const ClusterLayout<N, C> lay(NR, NC, cpc, c->L, cs);
+    const ClusterLayout<N, C> lay(NR, NC, cpc, c->L, cs, cluster_six<N>(c));
     if (sizeof(float) * (size_t)lay.gro * (c->L >> 4) > 8 * 1024) continue;      // scanned once per update
     if (sizeof(float) * (size_t)NR * cpc > sizeof(float2) * (size_t)(N / C) * (N + 1)) continue;   // W aliases the row slab
     if (lay.total > (size_t)c->max_smem_optin) continue;
-    auto k = fpm_update_cluster_kernel<N, C, 512>;
+    auto k = cluster_kernel_for<N, C>(c);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) { cudaGetLastError(); continue; }
     if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
     cudaLaunchConfig_t cfg;
@@ -450,7 +465,7 @@ static int select_variant(fpmb200_ctx* c) {
     const int want = c->cluster_req ? c->cluster_req : (N == 256 ? 8 : (N == 128 && c->n_tiles * 4 <= c->sm_count) ? 4 : 1);
     bool ok = false;
     int max_clusters = 0;
-#ifndef FPM_DEV_FAST
+#if !defined(FPM_DEV_FAST) || defined(FPM_DEV_CLUSTER)
     if (N == 256 && want == 8) ok = cluster_fits<256, 8>(c, &c->cpc, &c->cs, &c->smem_bytes);
     else if (N == 128 && want == 4) {
       ok = cluster_fits<128, 4>(c, &c->cpc, &c->cs, &c->smem_bytes, &max_clusters);
@@ -465,7 +480,8 @@ static int select_variant(fpmb200_ctx* c) {
     if (ok) {
       c->cluster = want;
       snprintf(c->variant, sizeof c->variant,
-               "fpm_update_cluster_kernel<N=%d,cluster=%d> bbox=[%d..%d]x[%d..%d] cols/CTA=%d maxcell=%dx16 smem=%zuB", N, want,
+               "fpm_update_cluster_kernel<N=%d,cluster=%d%s%s> bbox=[%d..%d]x[%d..%d] cols/CTA=%d maxcell=%dx16 smem=%zuB", N, want,
+               (N == 128 && cluster_six<128>(c)) ? ",window=smem,pruned radix-16" : "", "",
                ylo, yhi, xlo, xhi, c->cpc, 1 << c->cs, c->smem_bytes);
       return FPMB200_OK;
     }
@@ -725,7 +741,7 @@ static int launch_update(fpmb200_ctx* c, const UpdateParams& p, int n_blocks, cu
 
 template <int N, int C>
 static int launch_cluster(fpmb200_ctx* c, const UpdateParams& p, int n_tiles, cudaStream_t st) {
-  auto k = fpm_update_cluster_kernel<N, C, 512>;
+  auto k = cluster_kernel_for<N, C>(c);
   CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -951,7 +967,7 @@ static int run_updates(fpmb200_ctx* c, int first, int n, int slot_begin, int n_u
   CK(cudaSetDevice(c->device));
   if (c->cluster > 1) {
     p.ocp = c->cpc;
-#ifndef FPM_DEV_FAST
+#if !defined(FPM_DEV_FAST) || defined(FPM_DEV_CLUSTER)
     if (c->N == 256 && c->cluster == 8) return launch_cluster<256, 8>(c, p, n, st);
     if (c->N == 128 && c->cluster == 4) return launch_cluster<128, 4>(c, p, n, st);
     if (c->N == 128 && c->cluster == 2) return launch_cluster<128, 2>(c, p, n, st);
