@@ -12,8 +12,20 @@
 //   max|objF| (fpmMain.cpp:460,467): the grid of cell maxima is distributed by cell row (cell row a lives in CTA
 //   a mod C); partial maxima of the touched cells are merged with DSMEM atomics, the slice maxima and max|P| are
 //   exchanged through per-rank slots.
-//   The spectrum window is read and written with plain coalesced loads/stores (each CTA touches only its own
-//   columns within an update; barrier.cluster orders them between updates).
+//   The spectrum window: narrow boxes on 128 x 128 tiles (SIX instances) keep each CTA's column slice of the window in
+//   shared memory, double-buffered; C2 forwards every new value into the shared memory of the CTA that owns its column
+//   in the NEXT window (st.async + that CTA's wbar), the part of the next slice outside this update's rectangle is read
+//   from the spectrum by threads without a column item.  Other boxes read their slice from the spectrum (L2) in S1 and
+//   C2.  The spectrum itself is written with plain coalesced stores in C2 (each CTA touches only its own columns within
+//   an update; the release / acquire pair of ubar orders them between updates).
+//   Threads without a column item in S1 / S2 ("helpers", the same count in every CTA) run beside the column stages:
+//   they arm the mbarriers, prefetch the next 1/I rows, fetch the untouched part of the next window slice and take the
+//   maxima of the edge pixels of the touched cells (which this update does not change).  The column threads meet at a
+//   named barrier between S1 and S2 instead of a block barrier.
+//   [r2] measured, one tile: 128 x 128 with a 35 x 35 box on 4 CTAs 9.3 -> 7.3 us per update (S1 4.0k -> 2.0k cycles,
+//   the edge loads off the critical path: D 1.7k -> 0.7k), on 2 CTAs 11.6 -> 9.9; 85 x 85 box 11.3 -> 10.3;
+//   256 x 256 on 8 CTAs 18.7 -> 17.9 (cfg5b), 19.2 -> 18.9 (cfg3).  The window slice on chip for the 85 x 85 box:
+//   12.2 us (1870 forwards per CTA and update cost more than the loads they save), not used.
 #pragma once
 #include <cooperative_groups.h>
 #include "fpm_update.cuh"
@@ -270,20 +282,25 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     float2* const Wcur = (u & 1) ? Wb1 : Wb0;
     float2* const Wnxt = (u & 1) ? Wb0 : Wb1;
     const uint32_t wnxt_a = smem_u32(Wnxt);
+    // Threads tid >= hlp0 have no column item in S1 / S2 (the same count in every CTA of the cluster): "helpers".  Their
+    // first warp also arms the barriers and issues the L2 prefetch, so that the S1 warps start on the butterflies at once.
+    const int hlp0 = min(NT, (R1 * CPC + 31) & ~31), hn = NT - hlp0;
+    const bool helpers = hn >= 64;
+    const int duty0 = helpers ? hlp0 : 0;
     if constexpr (WS) {
       // this update's slice is complete once the forwarded values of the previous C2 have landed (phase u - 1 of wbar);
       // whole warps wait: the warps of S1 and the one that arms the barriers
-      if (u > 0 && (warp == 0 || warp * 32 < R2 * ncl)) mbar_wait_cluster(wbar, (uint32_t)((u - 1) & 1), 4, u);
+      if (u > 0 && (warp == (duty0 >> 5) || warp * 32 < R2 * ncl)) mbar_wait_cluster(wbar, (uint32_t)((u - 1) & 1), 4, u);
     }
-    if (tid == 0) {   // arm this update's transfers (bytes may already be arriving: the counts are signed)
+    if (tid == duty0) {   // arm this update's transfers (bytes may already be arriving: the counts are signed)
       mbar_expect_tx(rbar, rbar_bytes);
       mbar_expect_tx(cbar, cbar_bytes);
       mbar_expect_tx(obar, (uint32_t)(sizeof(float) * C));
       if (has_next) mbar_expect_tx(wbar, (uint32_t)(sizeof(float2) * ovr * ovc));
     }
-    if (tid < R1) {   // next LED's 1/I rows of this CTA towards L2: R1 chunks of RPC*R2 floats
+    if ((unsigned)(tid - duty0) < (unsigned)R1) {   // next LED's 1/I rows of this CTA towards L2: R1 chunks of RPC*R2 floats
       const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
-      const float* nx = stack + (size_t)nslot * N * N + ((size_t)tid * N + rank * RPC) * R2;
+      const float* nx = stack + (size_t)nslot * N * N + ((size_t)(tid - duty0) * N + rank * RPC) * R2;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)(RPC * R2 * 4)) : "memory");
     }
     // the cells this rectangle touches are rebuilt from scratch: their owners clear them now, the partial
@@ -367,15 +384,14 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
         Wnxt[eb] = vb;
       }
     };
-    // Threads without a column item in S1 / S2 (the same count in every CTA of the cluster) take this side work while
-    // the column stages run; the column threads meet at a named barrier between S1 and S2.
-    const int hlp0 = min(NT, (R1 * CPC + 31) & ~31), hn = NT - hlp0;
-    const bool helpers = hn >= 64;
+    // Threads without a column item in S1 / S2 take this side work while the column stages run; the column threads
+    // meet at a named barrier between S1 and S2.
     if (!helpers || tid >= hlp0) {                           // (without helper threads: everybody, ahead of S1)
       const int t0 = helpers ? tid - hlp0 : tid, tn = helpers ? hn : NT;
       if (has_next) next_slice(t0, tn);
       edge_maxima(t0, tn);
     }
+    FPM_TICK(0);
     // ===== S1: pending pupil update (fpmMain.cpp:470-475), Phi = O*P, cols stage A (inverse) on this CTA's columns =====
     if (!helpers || tid < hlp0) {
       float pm2 = 0.f;
