@@ -289,14 +289,15 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     const int duty0 = helpers ? hlp0 : 0;
     if constexpr (WS) {
       // this update's slice is complete once the forwarded values of the previous C2 have landed (phase u - 1 of wbar);
-      // whole warps wait: the warps of S1 and the one that arms the barriers
-      if (u > 0 && (warp == (duty0 >> 5) || warp * 32 < R2 * ncl)) mbar_wait_cluster(wbar, (uint32_t)((u - 1) & 1), 4, u);
+      // the warps of S1 wait (whole warps)
+      if (u > 0 && warp * 32 < R2 * ncl) mbar_wait_cluster(wbar, (uint32_t)((u - 1) & 1), 4, u);
     }
     if (tid == duty0) {   // arm this update's transfers (bytes may already be arriving: the counts are signed)
       mbar_expect_tx(rbar, rbar_bytes);
       mbar_expect_tx(cbar, cbar_bytes);
       mbar_expect_tx(obar, (uint32_t)(sizeof(float) * C));
-      if (has_next) mbar_expect_tx(wbar, (uint32_t)(sizeof(float2) * ovr * ovc));
+      // (wbar is armed after S3: with nothing to forward its phase completes at once, and a warp that has not polled the
+      //  previous phase yet would then see that parity as the current, incomplete phase and wait for ever)
     }
     if ((unsigned)(tid - duty0) < (unsigned)R1) {   // next LED's 1/I rows of this CTA towards L2: R1 chunks of RPC*R2 floats
       const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
@@ -506,6 +507,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       for (int k1 = 0; k1 < R1; ++k1) rp[R2 * k1] = twmul<true>(v[k1], twA[k1 * R2 + j0]);
     }
     __syncthreads();
+    if (tid == 0 && has_next) mbar_expect_tx(wbar, (uint32_t)(sizeof(float2) * ovr * ovc));   // every waiter of the previous phase is past it
     FPM_TICK(3);
     // ===== S4: rows stage B (inverse) + amplitude replacement (fpmMain.cpp:378-393) + rows stage B' (forward) =====
 #pragma unroll

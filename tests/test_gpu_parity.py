@@ -538,6 +538,29 @@ def test_cluster_kernel(name, ctas, n_leds):
     a.close(), b.close()
 
 
+@pytest.mark.timeout(120, method="thread")
+@pytest.mark.parametrize("name,ctas", [("cfg2_fLEDc_np128", 2), ("cfg2_fLEDc_np128", 4), ("cfg5_cellscope2_np128", 4), ("cfg5b_cellscope2_np256", 8)])
+def test_cluster_kernel_repeated_runs(name, ctas):
+    """Persistent launches of the cluster kernel over whole iterations, repeated: the window slices forwarded between the
+    CTAs (st.async + the receiver's mbarrier) include LED steps after which a CTA's next slice lies outside the current
+    rectangle -- nothing to forward, the barrier phase completes when it is armed.  Arming it before every waiter of the
+    previous phase had polled made that waiter skip a phase and the launch never finished (timing dependent; found with
+    tools/dev_stress_cluster.py).  Every run must finish and give the same bits."""
+    c = T.Case(name, 1)
+    for n_tiles in (1, 5):
+        ctx = c.make_ctx(n_tiles=n_tiles, cluster=ctas)
+        assert "cluster=%d" % ctas in ctx.variant
+        ref = None
+        for rep in range(6):
+            ctx.init_tiles(); ctx.run(2); ctx.sync()
+            got = ctx.download(n_tiles - 1, objCrop=False)
+            if ref is None:
+                ref = got
+            else:
+                assert all(np.array_equal(a, b) for a, b in zip(got, ref) if a is not None)
+        ctx.close()
+
+
 def test_steps_equal_run_bitwise():
     """n_leds single-update launches == one persistent launch, bit for bit (state round-trips exactly)."""
     c = T.Case("cfg1_mono_np64", 6, 30)
