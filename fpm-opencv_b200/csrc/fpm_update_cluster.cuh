@@ -304,15 +304,28 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       const float* nx = stack + (size_t)nslot * N * N + ((size_t)(tid - duty0) * N + rank * RPC) * R2;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)(RPC * R2 * 4)) : "memory");
     }
-    // the cells this rectangle touches are rebuilt from scratch: their owners clear them now, the partial
-    // maxima arrive after the third cluster barrier of this update
     // (cell columns padded to a power of two: shifts instead of a runtime integer division on the per-update path)
     const int csh = 32 - __clz(ncc - 1);
-    for (int t = tid; t < (ncr << csh); t += NT) {
-      const int ta = t >> csh, tb = t & ((1 << csh) - 1);
-      const int a = cr0 + ta;
-      if (tb < ncc && a % C == rank) U[(a / C) * gc + cc0 + tb] = 0.f;
-    }
+    // max|objF| bookkeeping that does not depend on this update (side work, see below): once every rank's merges of the
+    // previous update have landed (ubar), the owners clear the cells this rectangle touches -- they are rebuilt from
+    // scratch, the partial maxima arrive after C2 -- and take the maximum of their share of the grid, i.e. of the cells
+    // this update leaves alone.
+    auto untouched_max = [&](int t0, int tn, bool own_barrier) {
+      for (int t = t0; t < (ncr << csh); t += tn) {
+        const int ta = t >> csh, tb = t & ((1 << csh) - 1);
+        const int a = cr0 + ta;
+        if (tb < ncc && a % C == rank) U[(a / C) * gc + cc0 + tb] = 0.f;
+      }
+      if (own_barrier) asm volatile("bar.sync 2, %0;" ::"r"(tn) : "memory");   // the helpers among themselves
+      else __syncthreads();
+      const int nown = (gr - rank + C - 1) / C;
+      const float4* U4 = reinterpret_cast<const float4*>(U);
+      const int n4 = (nown * gc) >> 2;
+      float m = 0.f;
+      for (int t = t0; t < n4; t += tn) { const float4 q = U4[t]; m = fmaxf(fmaxf(m, fmaxf(q.x, q.y)), fmaxf(q.z, q.w)); }
+      m = warp_max(m);
+      if (lane == 0) red[warp] = m;
+    };
 
     // Partial maxima of the touched cells, first part: the pixels of those cells outside the rectangle, which this update
     // does not change (shared out over the cluster): strips above / below (full width of the touched cells) and left /
@@ -387,8 +400,12 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     };
     // Threads without a column item in S1 / S2 take this side work while the column stages run; the column threads
     // meet at a named barrier between S1 and S2.
+    // Every rank's release of the previous update (its merges into the owners' grids and its spectrum stores) is
+    // acquired by whoever reads them: the side work, and the window loads of S1 / C2 when the slice is not on chip.
+    if (u > 0 && (!WS || !helpers || tid >= hlp0)) mbar_wait_cluster(ubar, (uint32_t)((u - 1) & 1), 2, u);
     if (!helpers || tid >= hlp0) {                           // (without helper threads: everybody, ahead of S1)
       const int t0 = helpers ? tid - hlp0 : tid, tn = helpers ? hn : NT;
+      untouched_max(t0, tn, helpers);
       if (has_next) next_slice(t0, tn);
       edge_maxima(t0, tn);
     }
@@ -685,7 +702,18 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
 #ifdef FPM_STAGE_TIMING
     FPM_TICK(12);
 #endif
-    for (int t = tid; t < (ncr << csh); t += NT) {           // merge into the owners' grids
+    // max|objF|^2 = max over the ranks of: the rank's partial maxima of the touched cells (its slice's new values, its share
+    // of the edge pixels) and the maximum of its share of the untouched cells (side work above) -- one exchange.
+    if (warp == 0) {
+      float m = (lane < NW) ? red[lane] : 0.f;
+      for (int t = lane; t < lay.tmr * lay.tmc; t += 32) m = fmaxf(m, __uint_as_float(Tm[t]));
+      m = warp_max(m);
+      if (lane < C) st_async_f1(mapa_u32(omx_a + 4u * rank, lane), m, mapa_u32(obar_a, lane));
+    }
+    __syncthreads();                                         // (warp 0 has read Tm)
+    // Off the critical path (the exchange is in flight): the partial maxima go to the owners' grids, which the NEXT
+    // update's side work scans after waiting for ubar.
+    for (int t = tid; t < (ncr << csh); t += NT) {
       const int ta = t >> csh, tb = t & ((1 << csh) - 1);
       if (tb >= ncc) continue;
       const unsigned v = Tm[ta * tmc + tb];
@@ -695,34 +723,19 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
         atomicMax(reinterpret_cast<unsigned*>(cluster.map_shared_rank(U, a % C)) + (a / C) * gc + cc0 + tb, v);
       }
     }
-    __syncthreads();
-    if (tid == 0) {
+    __syncthreads();                                         // (Tm is clear before the next update's side work fills it)
+#ifdef FPM_STAGE_TIMING
+    FPM_TICK(13);
+#endif
+    if (tid == duty0) {
       // one cluster-scope release for the whole CTA (cumulative over the barrier above): the merged maxima and this
-      // update's spectrum stores are visible to whoever observes the arrivals
+      // update's spectrum stores are visible to whoever observes the arrivals.  Issued by a helper thread: the ~1k cycles
+      // of the fence overlap the exchange and the next update's S1.
       asm volatile("fence.acq_rel.cluster;" ::: "memory");
 #pragma unroll
       for (int k = 0; k < C; ++k) mbar_arrive_remote(mapa_u32(ubar_a, k));
     }
-#ifdef FPM_STAGE_TIMING
-    FPM_TICK(13);
-#endif
-    mbar_wait_cluster(ubar, ph, 2, u);                            // every rank has merged
     FPM_TICK(9);
-    {
-      const int nown = (gr - rank + C - 1) / C;
-      const float4* U4 = reinterpret_cast<const float4*>(U);
-      const int n4 = (nown * gc) >> 2;
-      float m = 0.f;
-      for (int t = tid; t < n4; t += NT) { const float4 q = U4[t]; m = fmaxf(fmaxf(m, fmaxf(q.x, q.y)), fmaxf(q.z, q.w)); }
-      m = warp_max(m);
-      if (lane == 0) red[warp] = m;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      float m = (lane < NW) ? red[lane] : 0.f;
-      m = warp_max(m);
-      if (lane < C) st_async_f1(mapa_u32(omx_a + 4u * rank, lane), m, mapa_u32(obar_a, lane));
-    }
     mbar_wait_cluster(obar, ph, 3, u);
     {
       float om2 = omx[0];
