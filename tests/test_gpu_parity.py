@@ -496,6 +496,43 @@ def test_phased_kernel_box_shapes(name, ell):
     ctx.close()
 
 
+@pytest.mark.timeout(180, method="thread")
+@pytest.mark.parametrize("ctas", [4, 2])
+@pytest.mark.parametrize("ell", [(3, 5.0, -2, 5.0),       # 11 x 11 off-centre: narrow instance, three columns per CTA (four CTAs: 3, 3, 3, 2)
+                                 (0, 1.0, 0, 1.0),        # 3 x 3: with four CTAs the last one owns no column at all
+                                 (8, 9.0, -6, 11.0),      # 19 x 23 off-centre, one-sided in x: narrow instance
+                                 (0, 30.0, 0, 30.0),      # 61 x 61: wide instance (window in L2), helper threads
+                                 (0, 60.0, 0, 60.0)])     # 121 x 121: every thread has a column item, no helper threads
+def test_cluster_kernel_box_shapes(ell, ctas):
+    """fpm_update_cluster_kernel over the shapes its work decomposition distinguishes: narrow boxes (window slice on chip,
+    forwarded between the CTAs; six-sample butterflies) and wide ones, CTAs without columns, with and without helper
+    threads; windows at the spectrum border and far jumps among the LEDs (nothing to forward); 2 passes in one
+    persistent launch against the oracle."""
+    c = T.Case("cfg2_fLEDc_np128", 6, 14)
+    N = c.N
+    c.cx[10:14] = np.array([0, c.L - N, 3, c.L - N - 1], np.int16)
+    c.cy[10:14] = np.array([0, c.L - N, c.L - N - 2, 1], np.int16)
+    y, x = np.mgrid[0:N, 0:N]
+    yw, xw = np.where(y < N // 2, y, y - N), np.where(x < N // 2, x, x - N)
+    x0, ax, y0, ay = ell
+    S = ((((xw - x0) / ax) ** 2 + ((yw - y0) / ay) ** 2) <= 1).astype(np.float32)
+    try:
+        ctx = c.make_ctx(support=S, cluster=ctas)
+    except RuntimeError as e:
+        pytest.skip("no %d-CTA cluster for this box: %s" % (ctas, e))
+    assert "cluster=%d" % ctas in ctx.variant, ctx.variant
+    st = orc.State(orc.init_state(c.stack, c.L, c.r).objFc, S.astype(np.complex128), S.astype(np.float64))
+    ctx.upload_state(0, T.corner(st.objFc), st.P)
+    for _ in range(2):
+        for k in range(len(c.cx)):
+            orc.update(st, c.stack[k], int(c.cx[k]), int(c.cy[k]), c.cfg.delta1, c.cfg.delta2, c.cfg.eps, 1)
+    ctx.run(2)
+    ctx.finalize()
+    e = compare(ctx, st)
+    note("cluster kernel support %s: rel-L2 objF %.2e pupil %.2e [%s]" % (ell, e[0], e[1], ctx.variant[:110]))
+    ctx.close()
+
+
 @pytest.mark.parametrize("name", ["cfg1_mono_np64", "cfg7_mono_np90"])
 def test_windows_touching_the_spectrum_border(name):
     """Crop origins 0 and Nlarge-Np (the legal extremes, fpmMain.cpp:157-165)."""
