@@ -30,6 +30,10 @@
 #include <cooperative_groups.h>
 #include "fpm_update.cuh"
 
+#ifndef FPM_TICK_TID
+#define FPM_TICK_TID 0        // the thread whose stage clocks the timing build reports
+#endif
+
 namespace fpm {
 namespace cg = cooperative_groups;
 
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   const int cpc_inv = (65536 + CPC - 1) / CPC;
   const int jc0 = rank * CPC;
   const int ncl = max(0, min(CPC, NC - jc0));              // columns this CTA really has
+  const int ncl_inv = ncl ? (65536 + ncl - 1) / ncl : 0;
   const int gc = L >> 4, gr = L >> p.cs;
   // column work items (group, local column) of this thread: R1 * ncl <= 16 * 32 = NT, so every column stage is a single
   // round and the item index is computed once (a runtime integer division per stage and update sits on the critical path)
@@ -296,18 +301,24 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
       // the warps of S1 wait (whole warps)
       if (u > 0 && warp * 32 < R2 * ncl) mbar_wait_cluster(wbar, (uint32_t)((u - 1) & 1), 4, u);
     }
-    if (tid == duty0) {   // arm this update's transfers (bytes may already be arriving: the counts are signed)
-      mbar_expect_tx(rbar, rbar_bytes);
-      mbar_expect_tx(cbar, cbar_bytes);
-      mbar_expect_tx(obar, (uint32_t)(sizeof(float) * C));
-      // (wbar is armed after S3: with nothing to forward its phase completes at once, and a warp that has not polled the
-      //  previous phase yet would then see that parity as the current, incomplete phase and wait for ever)
-    }
-    if ((unsigned)(tid - duty0) < (unsigned)R1) {   // next LED's 1/I rows of this CTA towards L2: R1 chunks of RPC*R2 floats
-      const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
-      const float* nx = stack + (size_t)nslot * N * N + ((size_t)(tid - duty0) * N + rank * RPC) * R2;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)(RPC * R2 * 4)) : "memory");
-    }
+    auto duties = [&]() {
+      if (tid == duty0) {   // arm this update's transfers (bytes may already be arriving: the counts are signed)
+        mbar_expect_tx(rbar, rbar_bytes);
+        mbar_expect_tx(cbar, cbar_bytes);
+        mbar_expect_tx(obar, (uint32_t)(sizeof(float) * C));
+        // (wbar is armed after S3: with nothing to forward its phase completes at once, and a warp that has not polled the
+        //  previous phase yet would then see that parity as the current, incomplete phase and wait for ever)
+      }
+      if ((unsigned)(tid - duty0) < (unsigned)R1) {   // next LED's 1/I rows of this CTA towards L2: R1 chunks of RPC*R2 floats
+        const int nslot = (slot + 1 == p.n_leds) ? 0 : slot + 1;
+        const float* nx = stack + (size_t)nslot * N * N + ((size_t)(tid - duty0) * N + rank * RPC) * R2;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)(RPC * R2 * 4)) : "memory");
+      }
+    };
+    // The duty warp = the first helper warp.  It also issues the release fence at the end of the update (~1.3k cycles) and
+    // comes out of it late, so it stays out of the other helpers' barrier: they are the "side group".
+    const int sg0 = hlp0 + 32, sgn = hn - 32;
+    if (!helpers || (tid >= hlp0 && tid < sg0)) duties();
     // (cell columns padded to a power of two: shifts instead of a runtime integer division on the per-update path)
     const int csh = 32 - __clz(ncc - 1);
     // max|objF| bookkeeping that does not depend on this update (side work, see below): once every rank's merges of the
@@ -378,28 +389,23 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
           if (cell[k] >= 0) atomicMax(&Tm[cell[k]], __float_as_uint(fmaf(o[k].x, o[k].x, o[k].y * o[k].y)));
       }
     };
-    // the part of the next window's slice that this update does not touch: spectrum -> Wnxt.  Only those elements are
-    // enumerated -- the rows of the slice outside the rectangle (all columns), then the columns outside it on the other
-    // rows -- two loads in flight per thread.
+    // the part of the next window's slice that this update does not touch: spectrum -> Wnxt.  One slice element per
+    // thread and round (two rounds in flight); t / ncl by a 16-bit reciprocal, exact for t < 2048 (narrow boxes: t < 47 * 32).
     auto next_slice = [&](int t0, int tn) {
       const float2* wn = objFc + (size_t)r0n * L + c0n + jc0;
       const int dr = r0n - r0, dc = c0n + jc0 - c0;             // next-slice (rn, lc) is (rn + dr, lc + dc) of this rectangle
-      const int ra = max(0, -dr), rb = max(ra, min(NR, NR - dr));         // slice rows [ra, rb) lie inside the rectangle
-      const int la = min(ncl, max(0, -dc)), lb = max(la, min(ncl, NC - dc));   // slice columns [la, lb) likewise
-      const int wout = ncl - (lb - la);                          // columns outside per inside row
-      const int n1 = (NR - (rb - ra)) * ncl, ntot = n1 + (rb - ra) * wout;
-      auto locate = [&](int t) -> int {                          // item -> element index rn * CPC + lc
-        if (t < n1) { const int q = t / ncl, lc = t - q * ncl; return ((q < ra) ? q : q + (rb - ra)) * CPC + lc; }
-        const int t2 = t - n1, q = t2 / wout, w = t2 - q * wout;
-        return (ra + q) * CPC + ((w < la) ? w : w + (lb - la));
-      };
-      for (int t = t0; t < ntot; t += 2 * tn) {
-        const int ea = locate(t), eb = (t + tn < ntot) ? locate(t + tn) : ea;
-        const int rna = ea / CPC, rnb = eb / CPC;
-        const float2 va = __ldcg(wn + (size_t)rna * L + (ea - rna * CPC));
-        const float2 vb = __ldcg(wn + (size_t)rnb * L + (eb - rnb * CPC));
-        Wnxt[ea] = va;
-        Wnxt[eb] = vb;
+      const int n = NR * ncl;
+      for (int t = t0; t < n; t += 2 * tn) {
+        const int tb = t + tn;
+        const int rna = (t * ncl_inv) >> 16, lca = t - rna * ncl;
+        const int rnb = (tb * ncl_inv) >> 16, lcb = tb - rnb * ncl;
+        const bool fa = !((unsigned)(rna + dr) < (unsigned)NR && (unsigned)(lca + dc) < (unsigned)NC);
+        const bool fb = tb < n && !((unsigned)(rnb + dr) < (unsigned)NR && (unsigned)(lcb + dc) < (unsigned)NC);
+        float2 va = make_float2(0.f, 0.f), vb = va;
+        if (fa) va = __ldcg(wn + (size_t)rna * L + lca);
+        if (fb) vb = __ldcg(wn + (size_t)rnb * L + lcb);
+        if (fa) Wnxt[rna * CPC + lca] = va;
+        if (fb) Wnxt[rnb * CPC + lcb] = vb;
       }
     };
     // Threads without a column item in S1 / S2 take this side work while the column stages run; the column threads
@@ -407,9 +413,15 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     // Every rank's release of the previous update (its merges into the owners' grids and its spectrum stores) is
     // acquired by whoever reads them: the side work, and the window loads of S1 / C2 when the slice is not on chip.
     if (u > 0 && (!WS || !helpers || tid >= hlp0)) mbar_wait_cluster(ubar, (uint32_t)((u - 1) & 1), 2, u);
-    if (!helpers || tid >= hlp0) {                           // (without helper threads: everybody, ahead of S1)
-      const int t0 = helpers ? tid - hlp0 : tid, tn = helpers ? hn : NT;
+#ifdef FPM_TICK_SIDE          // (timing build reporting a helper thread: slots 14 / 2 / 3 = ubar wait / untouched maximum / duties)
+    FPM_TICK(14);
+#endif
+    if (!helpers || tid >= sg0) {                            // (without helper threads: everybody, ahead of S1)
+      const int t0 = helpers ? tid - sg0 : tid, tn = helpers ? sgn : NT;
       untouched_max(t0, tn, helpers);
+#ifdef FPM_TICK_SIDE
+      FPM_TICK(2);
+#endif
       if (has_next) next_slice(t0, tn);
       if (!EDGE_LATE || !helpers) edge_maxima(t0, tn);
     }
@@ -754,7 +766,7 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
   }
 
 #ifdef FPM_STAGE_TIMING
-  if (tid == 0 && blockIdx.x == 0) {
+  if (tid == FPM_TICK_TID && blockIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) p.stage_clk[k] += tacc_[k];
   }

@@ -461,8 +461,12 @@ static int select_variant(fpmb200_ctx* c) {
   c->cluster = 1;
   {
     // default: 256x256 tiles always (the field does not fit one SM otherwise); 128x128 tiles when there are so few
-    // tiles that a quarter of the SMs would idle anyway (single-tile runs: lower latency per update)
-    const int want = c->cluster_req ? c->cluster_req : (N == 256 ? 8 : (N == 128 && c->n_tiles * 4 <= c->sm_count) ? 4 : 1);
+    // tiles that SMs would idle anyway (lower latency per update): four CTAs per tile up to a quarter of the SMs
+    // (6.5 us per update against 10.1 us on one CTA), two CTAs per tile up to half of them when the box is narrow (window
+    // slice on chip: 9.0 us) -- e.g. the 40 tiles a GPU holds of a 2560 x 2160 frame spread over eight GPUs
+    const int want = c->cluster_req ? c->cluster_req
+                   : (N == 256 ? 8 : (N == 128 && c->n_tiles * 4 <= c->sm_count) ? 4
+                   : (N == 128 && c->n_tiles * 2 <= c->sm_count && cluster_six<128>(c)) ? 2 : 1);
     bool ok = false;
     int max_clusters = 0;
 #if !defined(FPM_DEV_FAST) || defined(FPM_DEV_CLUSTER)
@@ -472,7 +476,10 @@ static int select_variant(fpmb200_ctx* c) {
       // the library's own choice only pays when every tile's cluster is resident at once (GPC boundaries strand SMs)
       if (ok && !c->cluster_req && c->n_tiles > max_clusters) ok = false;
     }
-    else if (N == 128 && want == 2) ok = cluster_fits<128, 2>(c, &c->cpc, &c->cs, &c->smem_bytes);
+    else if (N == 128 && want == 2) {
+      ok = cluster_fits<128, 2>(c, &c->cpc, &c->cs, &c->smem_bytes, &max_clusters);
+      if (ok && !c->cluster_req && c->n_tiles > max_clusters) ok = false;
+    }
     else
 #endif
     if (want != 1 && c->cluster_req)
