@@ -59,7 +59,8 @@ int fpmb200_tiles_alloc(fpmb200_ctx* ctx, int n_tiles, int Np, int Nlarge, int n
 int fpmb200_set_params(fpmb200_ctx* ctx, float delta1, float delta2, float eps, int literal_scalar);
 
 /* CTAs per tile of the update kernel: 0 = let the library choose (default: a cluster of 8 CTAs with the field in
- * distributed shared memory for Np=256, one CTA per tile otherwise), 1 = one CTA per tile, 2 / 4 (Np=128) or
+ * distributed shared memory for Np=256; Np=128: 4 CTAs per tile while at most a quarter of the SMs' worth of tiles is
+ * allocated, 2 up to half of them when the pupil box is narrow, one CTA per tile otherwise), 1 = one CTA per tile, 2 / 4 (Np=128) or
  * 8 (Np=256) = a thread-block cluster per tile (lower single-tile latency; fewer tiles in flight).  The
  * reference has no counterpart: it is the choice its OpenCL queue makes implicitly (fpmMain.cpp:345-476). */
 int fpmb200_set_cluster(fpmb200_ctx* ctx, int ctas_per_tile);

@@ -57,11 +57,11 @@ for name in names:
             # ticks of fpm_update_cluster_kernel in program order (a tick right after a wait holds the wait)
             print(name, "tiles", n_tiles, ctx.variant)
             tot = v[0:16].sum()
-            for k, lab in ((11, "top"), (0, "wbar wait, U clear (helpers: arm, prefetch)"), (1, "S1 P+=Q, O*P, inv col A (+ named barrier)"),
+            for k, lab in ((11, "top"), (0, "wbar wait (helper threads: the side work)"), (1, "S1 P+=Q, O*P, inv col A (+ named barrier)"),
                            (14, "S2 inv col B + remote stores"), (2, "   wait: row slab"), (3, "S3 inv row A"), (4, "S4 inv row B + amplitude + fwd row B'"),
                            (15, "S5 fwd row A' + remote stores"), (5, "   wait: column slab"), (6, "S6 fwd col B'"), (7, "S7 fwd col A'"),
-                           (8, "C2 object update, Q, forwards"), (12, "D  partial cell maxima of the slice"), (13, "D  merge, fence, arrive"),
-                           (9, "   wait: all merged"), (10, "E  scan own cells, exchange, wait")):
+                           (8, "C2 object update, Q, forwards"), (12, "D  partial cell maxima of the slice"), (13, "D  reduce + send (warp 0), merge into the owners"),
+                           (9, "   release fence + arrivals (duty thread)"), (10, "E  wait: exchange of the rank maxima")):
                 print("   %-46s %8.0f cyc  %5.1f%%" % (lab, v[k], 100 * v[k] / tot))
             print("   total %.0f cycles/update (thread 0 of CTA 0)" % tot)
             ctx.close()
