@@ -7,25 +7,33 @@
 //       slice of P, Q = pending pupil increment, the support and a column slab  cslab[column][row position]
 //   row passes (S3,S4,S5 incl. the amplitude replacement):   CTA k owns N/C scrambled row positions,
 //       row slab  rslab[row][column]
-//   The two transposes between them are written straight into the owner's shared memory (DSMEM stores issued by
-//   the producing butterfly, lanes contiguous in the destination) and fenced by barrier.cluster.
+//   The two transposes between them are written straight into the owner's shared memory by the producing butterfly
+//   (st.async + the owner's mbarrier counts the bytes: no cluster-wide barrier, no fence on the data path).
 //   max|objF| (fpmMain.cpp:460,467): the grid of cell maxima is distributed by cell row (cell row a lives in CTA
-//   a mod C); partial maxima of the touched cells are merged with DSMEM atomics, the slice maxima and max|P| are
-//   exchanged through per-rank slots.
+//   a mod C).  Per update ONE exchange: every rank sends max(its partial maxima of the touched cells = its slice's new
+//   values + its share of the edge pixels, the maximum of its share of the untouched cells) to every rank.  The
+//   untouched-cell maximum and the edge pixels do not depend on the update and are taken beside the column stages; the
+//   merges of the partial maxima into the owners' grids (DSMEM atomics), the one release fence and the ubar arrivals
+//   follow while the exchange is in flight, and are acquired by the next update's side work.
 //   The spectrum window: narrow boxes on 128 x 128 tiles (SIX instances) keep each CTA's column slice of the window in
 //   shared memory, double-buffered; C2 forwards every new value into the shared memory of the CTA that owns its column
 //   in the NEXT window (st.async + that CTA's wbar), the part of the next slice outside this update's rectangle is read
 //   from the spectrum by threads without a column item.  Other boxes read their slice from the spectrum (L2) in S1 and
 //   C2.  The spectrum itself is written with plain coalesced stores in C2 (each CTA touches only its own columns within
 //   an update; the release / acquire pair of ubar orders them between updates).
-//   Threads without a column item in S1 / S2 ("helpers", the same count in every CTA) run beside the column stages:
-//   they arm the mbarriers, prefetch the next 1/I rows, fetch the untouched part of the next window slice and take the
-//   maxima of the edge pixels of the touched cells (which this update does not change).  The column threads meet at a
-//   named barrier between S1 and S2 instead of a block barrier.
-//   [r2] measured, one tile: 128 x 128 with a 35 x 35 box on 4 CTAs 9.3 -> 7.3 us per update (S1 4.0k -> 2.0k cycles,
-//   the edge loads off the critical path: D 1.7k -> 0.7k), on 2 CTAs 11.6 -> 9.9; 85 x 85 box 11.3 -> 10.3;
-//   256 x 256 on 8 CTAs 18.7 -> 17.9 (cfg5b), 19.2 -> 18.9 (cfg3).  The window slice on chip for the 85 x 85 box:
+//   Threads without a column item in S1 / S2 ("helpers", the same count in every CTA) run beside the column stages.  The
+//   first helper warp (duty warp) arms the mbarriers, prefetches the next 1/I rows and issues the release fence; the
+//   others (side group, own named barrier) clear + scan the untouched cells, fetch the untouched part of the next window
+//   slice and take the edge-pixel maxima (narrow boxes: beside S6 / S7).  The column threads meet at a named barrier
+//   between S1 and S2 (narrow boxes: S6 and S7 too) instead of a block barrier.
+//   Barrier rule (a hang was found the hard way): a barrier whose phase can complete the moment it is armed (wbar with
+//   nothing to forward) is armed only after a block barrier that every waiter of the previous phase has passed.
+//   [r2] measured, one tile: 128 x 128 with a 35 x 35 box on 4 CTAs 9.3 -> 6.5 us per update (S1 4.0k -> 1.7k cycles,
+//   the work after C2 4.8k -> 2.2k of which 1.2k overlap the exchange), on 2 CTAs 11.6 -> 9.0; 85 x 85 box 11.3 -> 9.8;
+//   256 x 256 on 8 CTAs 18.7 -> 17.5 (cfg5b), 19.2 -> 18.2 (cfg3).  The window slice on chip for the 85 x 85 box:
 //   12.2 us (1870 forwards per CTA and update cost more than the loads they save), not used.
+//   Also measured and dropped: the slice's partial cell maxima taken inside C2 (match.any + redux + one shared atomic per
+//   distinct cell of the warp instead of the W pass after C2): C2 1.55k -> 2.9k cycles at N = 128, 5.7k -> 9.6k at 256.
 #pragma once
 #include <cooperative_groups.h>
 #include "fpm_update.cuh"
@@ -259,8 +267,10 @@ __global__ void __launch_bounds__(NT, 1) fpm_update_cluster_kernel(const __grid_
     }
     __syncthreads();
   }
+  int slot_it = p.slot_begin % p.n_leds;
   for (int u = 0; u < p.n_updates; ++u) {
-    const int slot = (p.slot_begin + u) % p.n_leds;
+    const int slot = slot_it;                               // (p.slot_begin + u) % p.n_leds without the division
+    slot_it = (slot + 1 == p.n_leds) ? 0 : slot + 1;
     const short2 cr = cr_next, crn = cr_next2;
     cr_next = cr_next2;
     {
