@@ -22,7 +22,8 @@ in the full-FOV leg, the final gather.
             (SURVEY 8d's algorithmic 18*Np^2 bytes against the measured copy bandwidth, plus the DRAM bytes ncu
             actually saw) and `roofline_smem` are the secondary views.
 other legs: `single_tile` (configs[0], [1], [2]: latency of one tile), `stress` (configs[4]: cellscope2, 193 LEDs x 50
-            iterations), `full_fov` (configs[3]'s 2560x2160 frame: 320 tiles sharded strongly over the ranks).
+            iterations), `full_fov` (configs[3]'s 2560x2160 frame: 320 tiles sharded strongly over the ranks),
+            `full_fov_shares` (N = 1: the per-GPU share of that frame at 2 / 4 / 8 GPUs, run on this GPU).
 `--impl reference`: the reference's CPU path (1:1 OpenCV op-sequence mirror, oracle/cv2_mirror.py --
             the reference binary itself cannot be built here) on all host cores; loads no
             library of this repo.
@@ -474,6 +475,35 @@ def run_b200(args):
     fov_variant = fctx.variant
     fctx.close()
 
+    # ---- N = 1 only: the share one GPU holds of the same frame at 2 / 4 / 8 GPUs, run on this GPU in a context of that
+    #      size (the library's few-tiles policy picks the kernel: clusters of two CTAs per tile at 40 tiles).  The device
+    #      time of the strong-scaling leg at W GPUs is this number plus the gather; the 8-GPU lines of SCALE check it. ----
+    fov_shares = None
+    if world == 1:
+        fov_shares = []
+        for w in (2, 4, 8):
+            nl_w = (fov_tiles + w - 1) // w
+            sctx = fpmb200.Context(local)
+            sctx.tiles_alloc(nl_w, N, L, n_leds)
+            sctx.set_params(g["delta1"], g["delta2"], g["eps"], 1)
+            sctx.upload_leds(g["cx"], g["cy"])
+            sctx.upload_pupil_support(g["support"])
+            for t in range(nl_w):
+                sctx.upload_stack(t, distinct[t % len(distinct)])
+            passes = []
+            for rep in range(4):                      # first pass = warm-up
+                f0, f1 = ev(), ev()
+                f0.record(main)
+                sctx.init_tiles(0, nl_w, 1, sp)
+                sctx.run(iters, 0, nl_w, sp)
+                sctx.finalize(0, nl_w, sp)
+                f1.record(main)
+                torch.cuda.synchronize()
+                if rep:
+                    passes.append(f0.elapsed_time(f1))
+            fov_shares.append({"gpus": w, "tiles_per_gpu": nl_w, "recon_ms": float(np.median(passes)), "kernel": sctx.variant})
+            sctx.close()
+
     # ---- stress leg: BASELINE configs[4] (cellscope2 dome, 128x128 tiles, Nlarge 512, 193 LEDs, 50 iterations),
     #      148 tiles per GPU (one wave), weak scaling like the headline ----
     stress = None
@@ -601,6 +631,8 @@ def run_b200(args):
             "full_fov": {"frame": "2560x2160", "tiles": fov_tiles, "recon_ms": fov_ms, "recon_ms_passes": fov_pass, "gather_s": gather_s,
                          "updates_per_s": fov_tiles * n_leds * iters / (fov_ms * 1e-3), "scaling": "strong", "kernel": fov_variant},
         }
+        if fov_shares is not None:
+            line["full_fov_shares"] = fov_shares
         if stress is not None:
             line["stress"] = stress
         if single is not None:
