@@ -1,5 +1,7 @@
 # Round-2 closing measurement pass after the cluster-kernel rework (run under gpurun): bench line, configuration sweep,
 # stage table and ncu capture of the 4-CTA cluster kernel on one 128 x 128 tile.
+# Needs the developer timing build of the cluster kernels: make -C fpm-opencv_b200 lib/libfpmb200_fastd.so (built here, it
+# travels with the snapshot).  Protocol stress of the cluster kernels: timeout 120 python tools/dev_stress_cluster.py 20
 set -x
 mkdir -p gpurun_out
 timeout 500 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_final_bench.json 2> gpurun_out/r02_final_bench.err || exit 1
